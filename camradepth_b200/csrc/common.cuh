@@ -1,0 +1,79 @@
+// Shared device helpers for the camradepth_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define CRD_F32 0
+#define CRD_BF16 1
+
+extern unsigned long long g_crd_launches;   // counted by every launcher (crd_launch_count)
+
+#define CRD_LAUNCH_CHECK()                                   \
+  do {                                                       \
+    g_crd_launches++;                                        \
+    cudaError_t e__ = cudaPeekAtLastError();                 \
+    if (e__ != cudaSuccess) return (int)e__;                 \
+  } while (0)
+
+#define CRD_REQUIRE(cond) do { if (!(cond)) return -1000 - __LINE__; } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+template <typename T> struct TypeTag;
+template <> struct TypeTag<float> { static constexpr int id = CRD_F32; };
+template <> struct TypeTag<bf16> { static constexpr int id = CRD_BF16; };
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 8-element vector load/store (channels are always padded to multiples of 8)
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  uint4 r = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float gelu_f(float x) {            // exact erf GELU (nn.GELU default)
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+static inline int crd_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// dtype dispatch helpers for launchers
+#define CRD_DISPATCH_1(dt, T, ...)                          \
+  if ((dt) == CRD_F32) { typedef float T; __VA_ARGS__; }    \
+  else if ((dt) == CRD_BF16) { typedef bf16 T; __VA_ARGS__; } \
+  else return -2;

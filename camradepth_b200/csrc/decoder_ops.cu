@@ -1,0 +1,469 @@
+// Decoder pieces that are not plain contractions: bicubic x2 upsample
+// written straight into a channel slice of the concat buffer, the Cout=1 depth-head stencil, argmax
+// segmentation maps, the NCHW<->NHWC boundary converts and weight (un)packing.
+#include "common.cuh"
+#include "chan_reduce.cuh"
+#include "../../include/camradepth_b200.h"
+
+namespace {
+
+// PyTorch upsample_bicubic2d, align_corners=False, scale 2, A=-0.75 (utils.py:241):
+// even output 2y: taps rows y-2..y+1 with t=.75 ; odd output 2y+1: rows y-1..y+2 with t=.25
+__device__ __forceinline__ void bicubic_taps(int o, int& base, float (&cf)[4]) {
+  const float c25[4] = {-0.10546875f, 0.87890625f, 0.26171875f, -0.03515625f};
+  if (o & 1) {
+    base = (o >> 1) - 1;
+#pragma unroll
+    for (int i = 0; i < 4; i++) cf[i] = c25[i];
+  } else {
+    base = (o >> 1) - 2;
+#pragma unroll
+    for (int i = 0; i < 4; i++) cf[i] = c25[3 - i];
+  }
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+template <typename T>
+__global__ void bicubic_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C,
+                                   int ldx, int ldy) {
+  const int cvec = C / 8;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long total = (long long)B * Ho * Wo * cvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    long long pix = i / cvec;
+    const int ox = (int)(pix % Wo);
+    const int oy = (int)((pix / Wo) % Ho);
+    const int b = (int)(pix / ((long long)Wo * Ho));
+    int by, bx;
+    float cy[4], cx[4];
+    bicubic_taps(oy, by, cy);
+    bicubic_taps(ox, bx, cx);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+#pragma unroll
+    for (int iy = 0; iy < 4; iy++) {
+      const int sy = clampi(by + iy, 0, H - 1);
+#pragma unroll
+      for (int ix = 0; ix < 4; ix++) {
+        const int sx = clampi(bx + ix, 0, W - 1);
+        float v[8];
+        load8(x + (((long long)b * H + sy) * W + sx) * ldx + cv * 8, v);
+        const float wgt = cy[iy] * cx[ix];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = fmaf(wgt, v[j], acc[j]);
+      }
+    }
+    store8(y + pix * ldy + cv * 8, acc);
+  }
+}
+
+// weight with which output coordinate o reads input coordinate s (border clamping folded in)
+__device__ __forceinline__ float bicubic_weight(int o, int s, int n) {
+  int base;
+  float cf[4];
+  bicubic_taps(o, base, cf);
+  float w = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; i++) w += (clampi(base + i, 0, n - 1) == s) ? cf[i] : 0.f;
+  return w;
+}
+
+template <typename T>
+__global__ void bicubic_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int accumulate, int B, int H,
+                                   int W, int C, int lddy, int lddx) {
+  const int cvec = C / 8;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long total = (long long)B * H * W * cvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    long long pix = i / cvec;
+    const int sx = (int)(pix % W);
+    const int sy = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    float wy[8], wx[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      const int oy = 2 * sy - 3 + t, ox = 2 * sx - 3 + t;
+      wy[t] = (oy >= 0 && oy < Ho) ? bicubic_weight(oy, sy, H) : 0.f;
+      wx[t] = (ox >= 0 && ox < Wo) ? bicubic_weight(ox, sx, W) : 0.f;
+    }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+#pragma unroll
+    for (int ty = 0; ty < 8; ty++) {
+      if (wy[ty] == 0.f) continue;
+      const int oy = 2 * sy - 3 + ty;
+#pragma unroll
+      for (int tx = 0; tx < 8; tx++) {
+        if (wx[tx] == 0.f) continue;
+        const int ox = 2 * sx - 3 + tx;
+        float g[8];
+        load8(dy + (((long long)b * Ho + oy) * Wo + ox) * lddy + cv * 8, g);
+        const float wgt = wy[ty] * wx[tx];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = fmaf(wgt, g[j], acc[j]);
+      }
+    }
+    T* o = dx + pix * lddx + cv * 8;
+    if (accumulate) {
+      float old[8];
+      load8(o, old);
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[j] += old[j];
+    }
+    store8(o, acc);
+  }
+}
+
+// ------------------------------------------------------------------ 3x3 conv with a single output channel
+template <typename T>
+__global__ void conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                   const float* __restrict__ bias, float* __restrict__ y, int B, int H, int W,
+                                   int Cin, int ldx) {
+  extern __shared__ float ws[];   // [9][Cin]
+  for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const long long total = (long long)B * H * W;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const int ww = (int)(pix % W);
+    const int hh = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    float acc = bias ? bias[0] : 0.f;
+    for (int dh = -1; dh <= 1; dh++) {
+      const int h2 = hh + dh;
+      if (h2 < 0 || h2 >= H) continue;
+      for (int dw = -1; dw <= 1; dw++) {
+        const int w2 = ww + dw;
+        if (w2 < 0 || w2 >= W) continue;
+        const T* xp = x + (((long long)b * H + h2) * W + w2) * ldx;
+        const float* wp = ws + ((dh + 1) * 3 + (dw + 1)) * Cin;
+        for (int c = 0; c < Cin; c += 8) {
+          float v[8];
+          load8(xp + c, v);
+#pragma unroll
+          for (int j = 0; j < 8; j++) acc = fmaf(v[j], wp[c + j], acc);
+        }
+      }
+    }
+    y[pix] = acc;
+  }
+}
+
+template <typename T>
+__global__ void conv_c1_bwd_input_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                         T* __restrict__ dx, int B, int H, int W, int Cin, int lddx) {
+  const int cvec = Cin / 8;
+  const long long total = (long long)B * H * W * cvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    long long pix = i / cvec;
+    const int ww = (int)(pix % W);
+    const int hh = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+    for (int dh = -1; dh <= 1; dh++) {
+      const int h2 = hh - dh;
+      if (h2 < 0 || h2 >= H) continue;
+      for (int dw = -1; dw <= 1; dw++) {
+        const int w2 = ww - dw;
+        if (w2 < 0 || w2 >= W) continue;
+        const float g = dy[((long long)b * H + h2) * W + w2];
+        const float* wp = w + ((dh + 1) * 3 + (dw + 1)) * Cin + cv * 8;
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = fmaf(g, wp[j], acc[j]);
+      }
+    }
+    store8(dx + pix * lddx + cv * 8, acc);
+  }
+}
+
+template <typename T>
+__global__ void conv_c1_bwd_weight_kernel(const float* __restrict__ dy, const T* __restrict__ x, float* dw,
+                                          float* db, int B, int H, int W, int Cin, int ldx, long long ppb) {
+  extern __shared__ float red[];
+  const int cv = threadIdx.x, ry = threadIdx.y, rows = blockDim.y, cvec = blockDim.x;
+  const int b = blockIdx.y;
+  const long long N = (long long)H * W;
+  long long p0 = (long long)blockIdx.x * ppb, p1 = p0 + ppb;
+  if (p1 > N) p1 = N;
+  float acc[10][8];
+#pragma unroll
+  for (int q = 0; q < 10; q++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[q][j] = 0.f;
+  for (long long p = p0 + ry; p < p1; p += rows) {
+    const int hh = (int)(p / W), ww = (int)(p % W);
+    const float g = dy[(long long)b * N + p];
+    acc[9][0] += g;
+#pragma unroll
+    for (int dh = -1; dh <= 1; dh++) {
+      const int h2 = hh + dh;
+      if (h2 < 0 || h2 >= H) continue;
+#pragma unroll
+      for (int dw_ = -1; dw_ <= 1; dw_++) {
+        const int w2 = ww + dw_;
+        if (w2 < 0 || w2 >= W) continue;
+        float v[8];
+        load8(x + (((long long)b * H + h2) * W + w2) * ldx + cv * 8, v);
+        const int tap = (dh + 1) * 3 + (dw_ + 1);
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[tap][j] = fmaf(g, v[j], acc[tap][j]);
+      }
+    }
+  }
+  for (int q = 0; q < 10; q++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) red[(ry * cvec + cv) * 8 + j] = acc[q][j];
+    __syncthreads();
+    const int t = ry * cvec + cv, nt = rows * cvec;
+    for (int cc = t; cc < Cin; cc += nt) {
+      float s = 0.f;
+      for (int r = 0; r < rows; r++) s += red[r * cvec * 8 + cc];
+      if (q < 9) atomicAdd(dw + q * Cin + cc, s);
+      else if (db && cc == 0) atomicAdd(db, s * 1.0f);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void sigmoid_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx,
+                                   long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    float g[8], s[8];
+    load8(dy + i * 8, g);
+    load8(y + i * 8, s);
+#pragma unroll
+    for (int j = 0; j < 8; j++) g[j] = g[j] * s[j] * (1.f - s[j]);
+    store8(dx + i * 8, g);
+  }
+}
+
+template <typename T, typename TD>
+__global__ void argmax_map_kernel(const T* __restrict__ logits, int ld, int ncls, TD* dst, int ld_dst,
+                                  float* dst_f32, long long npix) {
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const T* lp = logits + pix * ld;
+    float best = to_f(lp[0]);
+    int bi = 0;
+    for (int c = 1; c < ncls; c++) {
+      const float v = to_f(lp[c]);
+      if (v > best) { best = v; bi = c; }
+    }
+    const float m = (float)bi / (float)ncls;
+    if (dst) dst[pix * ld_dst] = from_f<TD>(m);
+    if (dst_f32) dst_f32[pix] = m;
+  }
+}
+
+// ------------------------------------------------------------------ boundary layout converts
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int B, int C, int H,
+                                    int W, int ld) {
+  const long long hw = (long long)H * W;
+  const long long total = (long long)B * hw;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const long long b = pix / hw, r = pix - b * hw;
+    for (int c = 0; c < C; c++) dst[pix * ld + c] = from_f<T>(src[(b * C + c) * hw + r]);
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int B, int C, int H,
+                                    int W, int ld) {
+  const long long hw = (long long)H * W;
+  const long long total = (long long)B * hw;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const long long b = pix / hw, r = pix - b * hw;
+    for (int c = 0; c < C; c++) dst[(b * C + c) * hw + r] = to_f(src[pix * ld + c]);
+  }
+}
+
+template <typename T>
+__global__ void weight_pack_kernel(const float* __restrict__ w, T* __restrict__ dst, const int* __restrict__ map,
+                                   int Cout, int Cin, int taps, int Cin_p, int Cout_p, int mode) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % taps);
+    const int ci = (int)((i / taps) % Cin);
+    const int co = (int)(i / ((long long)taps * Cin));
+    const int cm = map ? map[ci] : ci;
+    const long long o = mode == 0 ? ((long long)co * taps + tap) * Cin_p + cm
+                                  : ((long long)cm * taps + tap) * Cout_p + co;
+    dst[o] = from_f<T>(w[i]);
+  }
+}
+__global__ void weight_unpack_grad_kernel(const float* __restrict__ dwp, float* __restrict__ grad,
+                                          const int* __restrict__ map, int Cout, int Cin, int taps, int Cin_p,
+                                          int accumulate) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % taps);
+    const int ci = (int)((i / taps) % Cin);
+    const int co = (int)(i / ((long long)taps * Cin));
+    const int cm = map ? map[ci] : ci;
+    const float v = dwp[((long long)co * taps + tap) * Cin_p + cm];
+    grad[i] = accumulate ? grad[i] + v : v;
+  }
+}
+
+// db[n] += sum_m dy[m][n]; blockDim = (cvec, rows)
+template <typename T>
+__global__ void col_sum_kernel(const T* __restrict__ dy, float* db, long long M, int N, int ld, long long ppb) {
+  extern __shared__ float red[];
+  const int cv = threadIdx.x, ry = threadIdx.y, rows = blockDim.y, cvec = blockDim.x;
+  long long p0 = (long long)blockIdx.x * ppb, p1 = p0 + ppb;
+  if (p1 > M) p1 = M;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) s[j] = 0.f;
+  for (long long p = p0 + ry; p < p1; p += rows) {
+    float v[8];
+    load8(dy + p * ld + cv * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; j++) s[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) red[(ry * cvec + cv) * 8 + j] = s[j];
+  __syncthreads();
+  const int t = ry * cvec + cv, nt = rows * cvec;
+  for (int c = t; c < N; c += nt) {
+    float a = 0.f;
+    for (int r = 0; r < rows; r++) a += red[r * cvec * 8 + c];
+    atomicAdd(db + c, a);
+  }
+}
+
+}  // namespace
+
+extern "C" int crd_bicubic2x_fwd(const void* x, void* y, int dtype, int B, int H, int W, int C, int ldx, int ldy,
+                                 crd_stream_t stream) {
+  CRD_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0);
+  const long long total = (long long)B * H * W * 4 * (C / 8);
+  if (total == 0) return 0;
+  CRD_DISPATCH_1(dtype, T, bicubic_fwd_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)x, (T*)y, B, H, W, C, ldx, ldy));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_bicubic2x_bwd(const void* dy, void* dx, int dtype, int accumulate, int B, int H, int W, int C,
+                                 int lddy, int lddx, crd_stream_t stream) {
+  CRD_REQUIRE(C % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0);
+  const long long total = (long long)B * H * W * (C / 8);
+  if (total == 0) return 0;
+  CRD_DISPATCH_1(dtype, T, bicubic_bwd_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)dy, (T*)dx, accumulate, B, H, W, C, lddy, lddx));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_conv3x3_c1_fwd(const void* x, int dtype, const float* w, const float* bias, float* y, int B,
+                                  int H, int W, int Cin, int ldx, crd_stream_t stream) {
+  CRD_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0 && Cin <= 1024);
+  const long long total = (long long)B * H * W;
+  if (total == 0) return 0;
+  CRD_DISPATCH_1(dtype, T, conv_c1_fwd_kernel<T><<<ew_blocks(total), 256, 9 * Cin * sizeof(float),
+                                                   (cudaStream_t)stream>>>((const T*)x, w, bias, y, B, H, W, Cin, ldx));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_conv3x3_c1_bwd(const float* dy, const void* x, int dtype, const float* w, void* dx, float* dw,
+                                  float* db, int B, int H, int W, int Cin, int ldx, int lddx,
+                                  crd_stream_t stream) {
+  CRD_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0 && Cin / 8 <= 256);
+  const long long total = (long long)B * H * W * (Cin / 8);
+  if (total == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dx) {
+    CRD_DISPATCH_1(dtype, T, conv_c1_bwd_input_kernel<T><<<ew_blocks(total), 256, 0, s>>>(
+                                 dy, w, (T*)dx, B, H, W, Cin, lddx));
+    CRD_LAUNCH_CHECK();
+  }
+  if (dw) {
+    ReduceLaunch r = plan_reduce(B, (long long)H * W, Cin);
+    const size_t smem = (size_t)r.block.x * r.block.y * 8 * sizeof(float);
+    CRD_DISPATCH_1(dtype, T, conv_c1_bwd_weight_kernel<T><<<r.grid, r.block, smem, s>>>(
+                                 dy, (const T*)x, dw, db, B, H, W, Cin, ldx, r.ppb));
+    CRD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+extern "C" int crd_sigmoid_bwd(const void* dy, const void* y, void* dx, int dtype, long long n,
+                               crd_stream_t stream) {
+  CRD_REQUIRE(n % 8 == 0);
+  if (n == 0) return 0;
+  CRD_DISPATCH_1(dtype, T, sigmoid_bwd_kernel<T><<<ew_blocks(n / 8), 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)dy, (const T*)y, (T*)dx, n / 8));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_argmax_map(const void* logits, int dtype, int ld, int ncls, void* dst, int dst_dtype,
+                              int ld_dst, float* dst_f32, long long npix, crd_stream_t stream) {
+  if (npix == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  CRD_DISPATCH_1(dtype, T, CRD_DISPATCH_1(dst_dtype, TD, argmax_map_kernel<T, TD><<<ew_blocks(npix), 256, 0, s>>>(
+                               (const T*)logits, ld, ncls, (TD*)dst, ld_dst, dst_f32, npix)));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int B, int C, int H, int W,
+                                int ld_dst, crd_stream_t stream) {
+  const long long total = (long long)B * H * W;
+  if (total == 0) return 0;
+  CRD_DISPATCH_1(dst_dtype, T, nchw_to_nhwc_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                                   src, (T*)dst, B, C, H, W, ld_dst));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_nhwc_to_nchw(const void* src, int src_dtype, float* dst, int B, int C, int H, int W,
+                                int ld_src, crd_stream_t stream) {
+  const long long total = (long long)B * H * W;
+  if (total == 0) return 0;
+  CRD_DISPATCH_1(src_dtype, T, nhwc_to_nchw_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                                   (const T*)src, dst, B, C, H, W, ld_src));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_weight_pack(const float* w, void* dst, int dst_dtype, const int* map, int Cout, int Cin,
+                               int taps, int Cin_p, int Cout_p, int mode, crd_stream_t stream) {
+  const long long total = (long long)Cout * Cin * taps;
+  if (total == 0) return 0;
+  CRD_DISPATCH_1(dst_dtype, T, weight_pack_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                                   w, (T*)dst, map, Cout, Cin, taps, Cin_p, Cout_p, mode));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_weight_unpack_grad(const float* dwp, float* grad, const int* map, int Cout, int Cin, int taps,
+                                      int Cin_p, int accumulate, crd_stream_t stream) {
+  const long long total = (long long)Cout * Cin * taps;
+  if (total == 0) return 0;
+  weight_unpack_grad_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(dwp, grad, map, Cout, Cin, taps,
+                                                                               Cin_p, accumulate);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_col_sum(const void* dy, int dtype, float* db, long long M, int N, int ld, crd_stream_t stream) {
+  CRD_REQUIRE(ld % 8 == 0 && N <= ld);
+  if (M == 0 || N == 0) return 0;
+  const int Np = (N + 7) / 8 * 8;
+  CRD_REQUIRE(Np <= ld && Np / 8 <= 256);
+  ReduceLaunch r = plan_reduce(1, M, Np);
+  const size_t smem = (size_t)r.block.x * r.block.y * 8 * sizeof(float);
+  CRD_DISPATCH_1(dtype, T, col_sum_kernel<T><<<dim3(r.grid.x), r.block, smem, (cudaStream_t)stream>>>(
+                               (const T*)dy, db, M, N, ld, r.ppb));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}

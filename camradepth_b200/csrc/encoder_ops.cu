@@ -1,0 +1,504 @@
+// Encoder block pieces that are not plain contractions:
+// depthwise 3x3 fused with the preceding GroupNorm apply, the max-pool "attention" score
+// (QK^T -> max over keys -> sum over heads, never materialising N x M), the rank-1 attention
+// output fused with the residual/DropPath add, and their backward passes.
+#include "common.cuh"
+#include "chan_reduce.cuh"
+#include "../../include/camradepth_b200.h"
+
+namespace {
+
+// ------------------------------------------------------------------ depthwise 3x3
+template <typename T>
+__global__ void dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ ab,
+                                  const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ y,
+                                  int B, int H, int W, int C) {
+  const int cvec = C / 8;
+  const long long total = (long long)B * H * W * cvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    long long pix = i / cvec;
+    const int ww = (int)(pix % W);
+    const int hh = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    const int c = cv * 8;
+    float a[8], sh[8], acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      a[j] = ab[((long long)b * C + c + j) * 2];
+      sh[j] = ab[((long long)b * C + c + j) * 2 + 1];
+      acc[j] = bias ? bias[c + j] : 0.f;
+    }
+#pragma unroll
+    for (int dh = -1; dh <= 1; dh++) {
+      const int h2 = hh + dh;
+      if (h2 < 0 || h2 >= H) continue;
+#pragma unroll
+      for (int dw = -1; dw <= 1; dw++) {
+        const int w2 = ww + dw;
+        if (w2 < 0 || w2 >= W) continue;
+        float v[8];
+        load8(x + (((long long)b * H + h2) * W + w2) * C + c, v);
+        const int tap = (dh + 1) * 3 + (dw + 1);
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = fmaf(w[(c + j) * 9 + tap], fmaf(a[j], v[j], sh[j]), acc[j]);
+      }
+    }
+    store8(y + pix * C + c, acc);
+  }
+}
+
+template <typename T>
+__global__ void dwconv_bwd_input_kernel(const T* __restrict__ dy, const float* __restrict__ w,
+                                        T* __restrict__ dxn, int B, int H, int W, int C) {
+  const int cvec = C / 8;
+  const long long total = (long long)B * H * W * cvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    long long pix = i / cvec;
+    const int ww = (int)(pix % W);
+    const int hh = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    const int c = cv * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+#pragma unroll
+    for (int dh = -1; dh <= 1; dh++) {
+      const int h2 = hh - dh;                 // output pixel that read this input with tap (dh,dw)
+      if (h2 < 0 || h2 >= H) continue;
+#pragma unroll
+      for (int dw = -1; dw <= 1; dw++) {
+        const int w2 = ww - dw;
+        if (w2 < 0 || w2 >= W) continue;
+        float g[8];
+        load8(dy + (((long long)b * H + h2) * W + w2) * C + c, g);
+        const int tap = (dh + 1) * 3 + (dw + 1);
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = fmaf(w[(c + j) * 9 + tap], g[j], acc[j]);
+      }
+    }
+    store8(dxn + pix * C + c, acc);
+  }
+}
+
+// dw[c][tap] += sum dy * xn(shifted); db[c] += sum dy.  blockDim = (cvec, rows), grid = (chunks, B)
+template <typename T>
+__global__ void dwconv_bwd_weight_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                         const float* __restrict__ ab, float* dw, float* db, int B, int H, int W,
+                                         int C, long long ppb) {
+  extern __shared__ float red[];
+  const int cv = threadIdx.x, ry = threadIdx.y, rows = blockDim.y, cvec = blockDim.x;
+  const int b = blockIdx.y;
+  const int c = cv * 8;
+  const long long N = (long long)H * W;
+  long long p0 = (long long)blockIdx.x * ppb, p1 = p0 + ppb;
+  if (p1 > N) p1 = N;
+  float a[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    a[j] = ab[((long long)b * C + c + j) * 2];
+    sh[j] = ab[((long long)b * C + c + j) * 2 + 1];
+  }
+  float acc[10][8];
+#pragma unroll
+  for (int q = 0; q < 10; q++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[q][j] = 0.f;
+  for (long long p = p0 + ry; p < p1; p += rows) {
+    const int hh = (int)(p / W), ww = (int)(p % W);
+    float g[8];
+    load8(dy + ((long long)b * N + p) * C + c, g);
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[9][j] += g[j];
+#pragma unroll
+    for (int dh = -1; dh <= 1; dh++) {
+      const int h2 = hh + dh;
+      if (h2 < 0 || h2 >= H) continue;
+#pragma unroll
+      for (int dw_ = -1; dw_ <= 1; dw_++) {
+        const int w2 = ww + dw_;
+        if (w2 < 0 || w2 >= W) continue;
+        float v[8];
+        load8(x + (((long long)b * H + h2) * W + w2) * C + c, v);
+        const int tap = (dh + 1) * 3 + (dw_ + 1);
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[tap][j] = fmaf(g[j], fmaf(a[j], v[j], sh[j]), acc[tap][j]);
+      }
+    }
+  }
+  for (int q = 0; q < 10; q++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) red[(ry * cvec + cv) * 8 + j] = acc[q][j];
+    __syncthreads();
+    const int t = ry * cvec + cv, nt = rows * cvec;
+    for (int cc = t; cc < C; cc += nt) {
+      float s = 0.f;
+      for (int r = 0; r < rows; r++) s += red[r * cvec * 8 + cc];
+      if (q < 9) atomicAdd(dw + cc * 9 + q, s);
+      else if (db) atomicAdd(db + cc, s);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ attention score
+// block: 64 tokens of one sample; loop heads; per head stage q[64][hd] and key chunks k[64][hd] in smem.
+constexpr int ATN = 64, AMK = 64;
+template <typename T>
+__global__ void __launch_bounds__(256) attn_qkmax_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k,
+                                                             float* __restrict__ s, unsigned short* __restrict__ idx,
+                                                             int B, int N, int M, int C, int heads, float scale) {
+  extern __shared__ float sm[];
+  const int hd = C / heads;
+  const int hdp = hd + 1;
+  float* qs = sm;                 // [ATN][hdp]
+  float* ks = sm + ATN * hdp;     // [AMK][hdp]
+  const int b = blockIdx.y;
+  const int n0 = blockIdx.x * ATN;
+  const int tid = threadIdx.x;
+  const int nl = tid >> 2, kl = tid & 3;
+  float total = 0.f;
+  for (int h = 0; h < heads; h++) {
+    __syncthreads();
+    for (int i = tid; i < ATN * hd; i += 256) {
+      const int r = i / hd, dd = i - r * hd;
+      const int n = n0 + r;
+      qs[r * hdp + dd] = (n < N) ? to_f(q[((long long)b * N + n) * C + h * hd + dd]) : 0.f;
+    }
+    float best = -INFINITY;
+    int besti = 0;
+    for (int mc = 0; mc < M; mc += AMK) {
+      __syncthreads();
+      for (int i = tid; i < AMK * hd; i += 256) {
+        const int r = i / hd, dd = i - r * hd;
+        const int m = mc + r;
+        ks[r * hdp + dd] = (m < M) ? to_f(k[((long long)b * M + m) * C + h * hd + dd]) : 0.f;
+      }
+      __syncthreads();
+      const int mend = min(AMK, M - mc);
+      for (int r = kl; r < mend; r += 4) {
+        float dot = 0.f;
+        const float* qp = qs + nl * hdp;
+        const float* kp = ks + r * hdp;
+#pragma unroll 8
+        for (int dd = 0; dd < hd; dd++) dot = fmaf(qp[dd], kp[dd], dot);
+        if (dot > best) { best = dot; besti = mc + r; }
+      }
+    }
+    // combine the 4 key-lanes (first occurrence wins ties)
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    total += best;
+    const int n = n0 + nl;
+    if (kl == 0 && n < N) idx[((long long)b * heads + h) * N + n] = (unsigned short)besti;
+  }
+  const int n = n0 + nl;
+  if (kl == 0 && n < N) s[(long long)b * N + n] = total * scale;
+}
+
+template <typename T>
+__global__ void attn_qkmax_bwd_kernel(const float* __restrict__ ds, const T* __restrict__ q,
+                                      const T* __restrict__ k, const unsigned short* __restrict__ idx,
+                                      T* __restrict__ dq, float* dk, int B, int N, int M, int C, int heads,
+                                      float scale) {
+  const int cvec = C / 8;
+  const int hd = C / heads;
+  const long long total = (long long)B * N * cvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    const long long tok = i / cvec;
+    const int b = (int)(tok / N);
+    const int n = (int)(tok - (long long)b * N);
+    const int c = cv * 8;
+    const int h = c / hd;           // hd is a multiple of 8
+    const int m = idx[((long long)b * heads + h) * N + n];
+    const float g = ds[tok] * scale;
+    float kv[8], qv[8], o[8];
+    load8(k + ((long long)b * M + m) * C + c, kv);
+    load8(q + tok * C + c, qv);
+#pragma unroll
+    for (int j = 0; j < 8; j++) o[j] = g * kv[j];
+    store8(dq + tok * C + c, o);
+    float* dkp = dk + ((long long)b * M + m) * C + c;
+#pragma unroll
+    for (int j = 0; j < 8; j++) atomicAdd(dkp + j, g * qv[j]);
+  }
+}
+
+// ------------------------------------------------------------------ proj applied to the token mean
+__global__ void attn_pv_fwd_kernel(const float* __restrict__ xbar, const float* __restrict__ Wp,
+                                   float* __restrict__ pv, int B, int C) {
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int o = warp; o < C; o += nw) {
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(Wp[(long long)o * C + c], xbar[(long long)b * C + c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) pv[(long long)b * C + o] = acc;
+  }
+}
+__global__ void attn_pv_bwd_w_kernel(const float* __restrict__ dpv, const float* __restrict__ xbar, float* dWp,
+                                     int B, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)C * C) return;
+  const int o = (int)(i / C), c = (int)(i % C);
+  float acc = 0.f;
+  for (int b = 0; b < B; b++) acc = fmaf(dpv[(long long)b * C + o], xbar[(long long)b * C + c], acc);
+  dWp[i] += acc;
+}
+__global__ void attn_pv_bwd_x_kernel(const float* __restrict__ dpv, const float* __restrict__ Wp,
+                                     float* __restrict__ dxbar, float scale, int B, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * C) return;
+  const int b = (int)(i / C), c = (int)(i % C);
+  float acc = 0.f;
+  for (int o = 0; o < C; o++) acc = fmaf(Wp[(long long)o * C + c], dpv[(long long)b * C + o], acc);
+  dxbar[i] = acc * scale;
+}
+
+__global__ void attn_out_residual_kernel(const float* __restrict__ x, const float* __restrict__ pv,
+                                         const float* __restrict__ s, const float* __restrict__ bp,
+                                         const float* __restrict__ dp, float* __restrict__ xout, int B, int N,
+                                         int C) {
+  const int c4 = C / 4;
+  const long long total = (long long)B * N * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) * 4;
+    const long long tok = i / c4;
+    const int b = (int)(tok / N);
+    const float sc = dp ? dp[b] : 1.f;
+    const float sv = s[tok];
+    const float4 xv = *reinterpret_cast<const float4*>(x + tok * C + c);
+    const float4 pvv = *reinterpret_cast<const float4*>(pv + (long long)b * C + c);
+    const float4 bv = *reinterpret_cast<const float4*>(bp + c);
+    float4 o;
+    o.x = xv.x + sc * fmaf(pvv.x, sv, bv.x);
+    o.y = xv.y + sc * fmaf(pvv.y, sv, bv.y);
+    o.z = xv.z + sc * fmaf(pvv.z, sv, bv.z);
+    o.w = xv.w + sc * fmaf(pvv.w, sv, bv.w);
+    *reinterpret_cast<float4*>(xout + tok * C + c) = o;
+  }
+}
+
+// ds[b][n] = dp[b] * sum_c dx[b][n][c] * pv[b][c]   (one warp per token)
+__global__ void attn_out_bwd_ds_kernel(const float* __restrict__ dx, const float* __restrict__ pv,
+                                       const float* __restrict__ dp, float* __restrict__ ds, int B, int N, int C) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= (long long)B * N) return;
+  const int b = (int)(warp / N);
+  float acc = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 g = *reinterpret_cast<const float4*>(dx + warp * C + c);
+    const float4 p = *reinterpret_cast<const float4*>(pv + (long long)b * C + c);
+    acc += g.x * p.x + g.y * p.y + g.z * p.z + g.w * p.w;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) ds[warp] = acc * (dp ? dp[b] : 1.f);
+}
+__global__ void attn_out_bwd_chan_kernel(const float* __restrict__ dx, const float* __restrict__ s, float* tmp,
+                                         int B, long long N, int C, long long ppb) {
+  chan_reduce2([&](int b, long long p, int c, float (&s0)[8], float (&s1)[8]) {
+    float g[8];
+    const long long tok = (long long)b * N + p;
+    load8(dx + tok * C + c, g);
+    const float sv = s[tok];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { s0[j] = fmaf(g[j], sv, s0[j]); s1[j] += g[j]; }
+  }, tmp, B, N, C, ppb);
+}
+__global__ void attn_out_bwd_fin_kernel(const float* __restrict__ tmp, const float* __restrict__ dp,
+                                        float* __restrict__ dpv, float* dbp, int B, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int b = 0; b < B; b++) {
+    const float sc = dp ? dp[b] : 1.f;
+    dpv[(long long)b * C + c] = sc * tmp[((long long)b * C + c) * 2];
+    acc += sc * tmp[((long long)b * C + c) * 2 + 1];
+  }
+  dbp[c] += acc;
+}
+
+template <typename T>
+__global__ void residual_add_kernel(const float* __restrict__ x, const T* __restrict__ y,
+                                    const float* __restrict__ dp, float* __restrict__ xout, int B, long long N,
+                                    int C) {
+  const int cvec = C / 8;
+  const long long total = (long long)B * N * cvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long tok = i / cvec;
+    const int b = (int)(tok / N);
+    const float sc = dp ? dp[b] : 1.f;
+    float xv[8], yv[8];
+    load8(x + i * 8, xv);
+    load8(y + i * 8, yv);
+#pragma unroll
+    for (int j = 0; j < 8; j++) xv[j] = fmaf(sc, yv[j], xv[j]);
+    store8(xout + i * 8, xv);
+  }
+}
+template <typename T>
+__global__ void scale_cast_kernel(const float* __restrict__ dx, const float* __restrict__ dp, T* __restrict__ dy,
+                                  int B, long long N, int C) {
+  const int cvec = C / 8;
+  const long long total = (long long)B * N * cvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long tok = i / cvec;
+    const int b = (int)(tok / N);
+    const float sc = dp ? dp[b] : 1.f;
+    float v[8];
+    load8(dx + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] *= sc;
+    store8(dy + i * 8, v);
+  }
+}
+template <typename T>
+__global__ void add_f32_kernel(float* __restrict__ dst, const T* __restrict__ src, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    load8(dst + i * 8, a);
+    load8(src + i * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[j] += b[j];
+    store8(dst + i * 8, a);
+  }
+}
+
+}  // namespace
+
+extern "C" int crd_dwconv3x3_fwd(const void* x, int dtype, const float* ab, const float* w, const float* bias,
+                                 void* y, int B, int H, int W, int C, crd_stream_t stream) {
+  CRD_REQUIRE(C % 8 == 0);
+  const long long total = (long long)B * H * W * (C / 8);
+  if (total == 0) return 0;
+  CRD_DISPATCH_1(dtype, T, dwconv_fwd_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)x, ab, w, bias, (T*)y, B, H, W, C));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_dwconv3x3_bwd_input(const void* dy, int dtype, const float* w, void* dxn, int B, int H, int W,
+                                       int C, crd_stream_t stream) {
+  CRD_REQUIRE(C % 8 == 0);
+  const long long total = (long long)B * H * W * (C / 8);
+  if (total == 0) return 0;
+  CRD_DISPATCH_1(dtype, T, dwconv_bwd_input_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)dy, w, (T*)dxn, B, H, W, C));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_dwconv3x3_bwd_weight(const void* dy, int dtype, const void* x, const float* ab, float* dw,
+                                        float* db, int B, int H, int W, int C, crd_stream_t stream) {
+  CRD_REQUIRE(C % 8 == 0 && C / 8 <= 256);
+  if (B == 0 || H * W == 0) return 0;
+  ReduceLaunch r = plan_reduce(B, (long long)H * W, C);
+  const size_t smem = (size_t)r.block.x * r.block.y * 8 * sizeof(float);
+  CRD_DISPATCH_1(dtype, T, dwconv_bwd_weight_kernel<T><<<r.grid, r.block, smem, (cudaStream_t)stream>>>(
+                               (const T*)dy, (const T*)x, ab, dw, db, B, H, W, C, r.ppb));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int crd_attn_qkmax_fwd(const void* q, const void* k, int dtype, float* s, unsigned short* idx, int B,
+                                  int N, int M, int C, int heads, float scale, crd_stream_t stream) {
+  CRD_REQUIRE(heads > 0 && C % heads == 0 && M >= 1 && M <= 65535);   // idx is uint16
+  if (B == 0 || N == 0) return 0;
+  const int hd = C / heads;
+  const size_t smem = (size_t)(ATN + AMK) * (hd + 1) * sizeof(float);
+  dim3 grid(crd_div_up(N, ATN), B);
+  CRD_DISPATCH_1(dtype, T, attn_qkmax_fwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
+                               (const T*)q, (const T*)k, s, idx, B, N, M, C, heads, scale));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_attn_qkmax_bwd(const float* ds, const void* q, const void* k, int dtype,
+                                  const unsigned short* idx, void* dq, float* dk, int B, int N, int M, int C,
+                                  int heads, float scale, crd_stream_t stream) {
+  CRD_REQUIRE(heads > 0 && C % heads == 0 && (C / heads) % 8 == 0);
+  const long long total = (long long)B * N * (C / 8);
+  if (total == 0) return 0;
+  CRD_DISPATCH_1(dtype, T, attn_qkmax_bwd_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                               ds, (const T*)q, (const T*)k, idx, (T*)dq, dk, B, N, M, C, heads, scale));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_attn_pv_fwd(const float* xbar, const float* Wp, float* pv, int B, int C, crd_stream_t stream) {
+  if (B == 0) return 0;
+  attn_pv_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(xbar, Wp, pv, B, C);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_attn_pv_bwd(const float* dpv, const float* xbar, const float* Wp, float* dWp, float* dxbar,
+                               float dxbar_scale, int B, int C, crd_stream_t stream) {
+  if (B == 0) return 0;
+  attn_pv_bwd_w_kernel<<<crd_div_up((long long)C * C, 256), 256, 0, (cudaStream_t)stream>>>(dpv, xbar, dWp, B, C);
+  CRD_LAUNCH_CHECK();
+  attn_pv_bwd_x_kernel<<<crd_div_up((long long)B * C, 256), 256, 0, (cudaStream_t)stream>>>(dpv, Wp, dxbar, dxbar_scale, B, C);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_attn_out_residual(const float* x, const float* pv, const float* s, const float* bp,
+                                     const float* dp, float* xout, int B, int N, int C, crd_stream_t stream) {
+  CRD_REQUIRE(C % 4 == 0);
+  const long long total = (long long)B * N * (C / 4);
+  if (total == 0) return 0;
+  attn_out_residual_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, pv, s, bp, dp, xout, B, N, C);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_attn_out_bwd(const float* dx, const float* pv, const float* s, const float* dp, float* ds,
+                                float* dpv, float* dbp, float* tmp, int B, int N, int C, crd_stream_t stream) {
+  CRD_REQUIRE(C % 8 == 0 && C / 8 <= 256);
+  if (B == 0 || N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  attn_out_bwd_ds_kernel<<<crd_div_up((long long)B * N * 32, 256), 256, 0, st>>>(dx, pv, dp, ds, B, N, C);
+  CRD_LAUNCH_CHECK();
+  cudaMemsetAsync(tmp, 0, (size_t)B * C * 2 * sizeof(float), st);
+  ReduceLaunch r = plan_reduce(B, N, C);
+  attn_out_bwd_chan_kernel<<<r.grid, r.block, r.smem, st>>>(dx, s, tmp, B, N, C, r.ppb);
+  CRD_LAUNCH_CHECK();
+  attn_out_bwd_fin_kernel<<<crd_div_up(C, 128), 128, 0, st>>>(tmp, dp, dpv, dbp, B, C);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_residual_add(const float* x, const void* y, int y_dtype, const float* dp, float* xout, int B,
+                                long long N, int C, crd_stream_t stream) {
+  CRD_REQUIRE(C % 8 == 0);
+  const long long total = (long long)B * N * (C / 8);
+  if (total == 0) return 0;
+  CRD_DISPATCH_1(y_dtype, T, residual_add_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                                 x, (const T*)y, dp, xout, B, N, C));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_scale_cast(const float* dx, const float* dp, void* dy, int dy_dtype, int B, long long N, int C,
+                              crd_stream_t stream) {
+  CRD_REQUIRE(C % 8 == 0);
+  const long long total = (long long)B * N * (C / 8);
+  if (total == 0) return 0;
+  CRD_DISPATCH_1(dy_dtype, T, scale_cast_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                                  dx, dp, (T*)dy, B, N, C));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_add_f32(float* dst, const void* src, int src_dtype, long long n, crd_stream_t stream) {
+  CRD_REQUIRE(n % 8 == 0);
+  if (n == 0) return 0;
+  CRD_DISPATCH_1(src_dtype, T, add_f32_kernel<T><<<ew_blocks(n / 8), 256, 0, (cudaStream_t)stream>>>(
+                                   dst, (const T*)src, n / 8));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}

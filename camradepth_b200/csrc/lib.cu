@@ -1,0 +1,14 @@
+// Library-level entry points: version, launch counter, capability probe.
+#include "common.cuh"
+#include "../../include/camradepth_b200.h"
+
+unsigned long long g_crd_launches = 0;
+
+extern "C" int crd_version(void) { return 1; }
+extern "C" unsigned long long crd_launch_count(void) { return g_crd_launches; }
+extern "C" int crd_has_tcgen05(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}

@@ -1,0 +1,230 @@
+// Fused losses and the multi-tensor diffGradNorm step (row a15).
+// All HBM-bound single-pass kernels: no boolean-index compaction, no host syncs, no per-tensor launches.
+#include "common.cuh"
+#include "../../include/camradepth_b200.h"
+
+namespace {
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (warp == 0) {
+    r = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.f;
+    r = warp_sum(r);
+  }
+  return r;   // valid in thread 0
+}
+
+__global__ void masked_l1_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                     float* acc, long long n) {
+  __shared__ float sh[32];
+  float s = 0.f, cnt = 0.f, sq = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float t = target[i];
+    if (t > 0.f) {
+      const float d = pred[i] - t;
+      const float a = fabsf(d);
+      s += (a < 1.f) ? 0.5f * d * d : a - 0.5f;
+      sq = fmaf(d, d, sq);
+      cnt += 1.f;
+    }
+  }
+  s = block_sum(s, sh);
+  cnt = block_sum(cnt, sh);
+  sq = block_sum(sq, sh);
+  if (threadIdx.x == 0) { atomicAdd(acc + 0, s); atomicAdd(acc + 1, cnt); atomicAdd(acc + 2, sq); }
+}
+
+__global__ void masked_l1_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                     const float* __restrict__ acc, const float* __restrict__ gout,
+                                     float* __restrict__ dpred, long long n) {
+  const float scale = gout[0] / acc[1];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float t = target[i];
+    float g = 0.f;
+    if (t > 0.f) {
+      const float d = pred[i] - t;
+      g = scale * fminf(fmaxf(d, -1.f), 1.f);
+    }
+    dpred[i] = g;
+  }
+}
+
+__global__ void ce_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target, float* acc,
+                              int B, int C, long long HW, int ignore_index) {
+  __shared__ float sh[32];
+  float s = 0.f, cnt = 0.f;
+  const long long total = (long long)B * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long t = target[i];
+    if (t != ignore_index) {
+      const long long b = i / HW, r = i - b * HW;
+      const float* lp = logits + b * C * HW + r;
+      float m = -INFINITY;
+      for (int c = 0; c < C; c++) m = fmaxf(m, lp[c * HW]);
+      float se = 0.f;
+      for (int c = 0; c < C; c++) se += __expf(lp[c * HW] - m);
+      s += m + __logf(se) - lp[t * HW];
+      cnt += 1.f;
+    }
+  }
+  s = block_sum(s, sh);
+  cnt = block_sum(cnt, sh);
+  if (threadIdx.x == 0) { atomicAdd(acc + 0, s); atomicAdd(acc + 1, cnt); }
+}
+
+__device__ __forceinline__ float focal_dce(float ce, float gamma) {
+  const float pt = __expf(-ce);
+  const float om = 1.f - pt;
+  // d/dce [(1-pt)^g * ce] = (1-pt)^g + g (1-pt)^(g-1) pt ce
+  return powf(om, gamma) + gamma * powf(om, gamma - 1.f) * pt * ce;
+}
+
+__global__ void ce_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+                              const float* __restrict__ acc, const float* __restrict__ gout, float gamma,
+                              float* __restrict__ dlogits, int B, int C, long long HW, int ignore_index) {
+  const float ce = acc[0] / acc[1];
+  const float coef = gout[0] * (gamma > 0.f ? focal_dce(ce, gamma) : 1.f) / acc[1];
+  const long long total = (long long)B * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long t = target[i];
+    const long long b = i / HW, r = i - b * HW;
+    const float* lp = logits + b * C * HW + r;
+    float* dp = dlogits + b * C * HW + r;
+    if (t == ignore_index) {
+      for (int c = 0; c < C; c++) dp[c * HW] = 0.f;
+      continue;
+    }
+    float m = -INFINITY;
+    for (int c = 0; c < C; c++) m = fmaxf(m, lp[c * HW]);
+    float se = 0.f;
+    for (int c = 0; c < C; c++) se += __expf(lp[c * HW] - m);
+    const float inv = 1.f / se;
+    for (int c = 0; c < C; c++) {
+      const float p = __expf(lp[c * HW] - m) * inv;
+      dp[c * HW] = coef * (p - (c == t ? 1.f : 0.f));
+    }
+  }
+}
+
+__global__ void loss_finalize_kernel(const float* __restrict__ acc, float* __restrict__ out, int kind,
+                                     float gamma) {
+  if (kind == 0) {
+    out[0] = acc[0] / acc[1];
+    out[1] = sqrtf(acc[2] / acc[1]);
+  } else {
+    const float ce = acc[0] / acc[1];
+    const float om = 1.f - __expf(-ce);
+    out[0] = powf(om, gamma) * ce;
+    out[1] = ce;
+  }
+}
+
+// ------------------------------------------------------------------ diffGradNorm
+__global__ void __launch_bounds__(256) mt_sumsq_kernel(const crd_opt_tensor* __restrict__ table,
+                                                       const crd_opt_chunk* __restrict__ chunks, float* sumsq) {
+  __shared__ float sh[32];
+  const crd_opt_chunk ck = chunks[blockIdx.x];
+  const crd_opt_tensor t = table[ck.tensor];
+  long long end = ck.start + CRD_OPT_CHUNK;
+  if (end > t.numel) end = t.numel;
+  float s = 0.f;
+  for (long long i = ck.start + threadIdx.x; i < end; i += blockDim.x) { const float g = t.g[i]; s = fmaf(g, g, s); }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) atomicAdd(sumsq + ck.tensor, s);
+}
+
+__global__ void __launch_bounds__(256) diffgradnorm_kernel(const crd_opt_tensor* __restrict__ table,
+                                                           const crd_opt_chunk* __restrict__ chunks,
+                                                           const float* __restrict__ sumsq,
+                                                           const float* __restrict__ egn_in, float* egn_out,
+                                                           float step_size, float beta1, float beta2, float eps) {
+  const crd_opt_chunk ck = chunks[blockIdx.x];
+  const crd_opt_tensor t = table[ck.tensor];
+  long long end = ck.start + CRD_OPT_CHUNK;
+  if (end > t.numel) end = t.numel;
+  // Gradient-norm correction (diffGradNorm.py:82-88); the branch is evaluated on the device.
+  const float gn = sqrtf(sumsq[ck.tensor]);
+  const float egn = 0.95f * egn_in[ck.tensor] + 0.05f * gn;
+  const float corr = (egn > gn) ? egn / (gn + 1e-8f) : 1.f;
+  if (ck.start == 0 && threadIdx.x == 0) egn_out[ck.tensor] = egn;
+  for (long long i = ck.start + threadIdx.x; i < end; i += blockDim.x) {
+    const float g = t.g[i];
+    const float m = beta1 * t.m[i] + (1.f - beta1) * (g * corr);
+    const float v = beta2 * t.v[i] + (1.f - beta2) * g * g;
+    const float denom = sqrtf(v) + eps;
+    const float dfc = 1.f / (1.f + __expf(-fabsf(t.prev[i] - g)));
+    t.m[i] = m;
+    t.v[i] = v;
+    t.prev[i] = g;
+    t.p[i] = t.p[i] - step_size * (m * dfc) / denom;
+  }
+}
+
+inline int red_blocks(long long n) {
+  long long b = (n + 1023) / 1024;
+  return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
+}
+
+}  // namespace
+
+extern "C" int crd_masked_l1_fwd(const float* pred, const float* target, float* acc, long long n,
+                                 crd_stream_t stream) {
+  if (n == 0) return 0;
+  masked_l1_fwd_kernel<<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>(pred, target, acc, n);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_masked_l1_bwd(const float* pred, const float* target, const float* acc, const float* gout,
+                                 float* dpred, long long n, crd_stream_t stream) {
+  if (n == 0) return 0;
+  masked_l1_bwd_kernel<<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>(pred, target, acc, gout, dpred, n);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_ce_fwd(const float* logits, const long long* target, float* acc, int B, int C, long long HW,
+                          int ignore_index, crd_stream_t stream) {
+  if ((long long)B * HW == 0) return 0;
+  ce_fwd_kernel<<<red_blocks((long long)B * HW), 256, 0, (cudaStream_t)stream>>>(logits, target, acc, B, C, HW,
+                                                                                 ignore_index);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_ce_bwd(const float* logits, const long long* target, const float* acc, const float* gout,
+                          float gamma, float* dlogits, int B, int C, long long HW, int ignore_index,
+                          crd_stream_t stream) {
+  if ((long long)B * HW == 0) return 0;
+  ce_bwd_kernel<<<red_blocks((long long)B * HW), 256, 0, (cudaStream_t)stream>>>(logits, target, acc, gout, gamma,
+                                                                                 dlogits, B, C, HW, ignore_index);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_loss_finalize(const float* acc, float* out, int kind, float gamma, crd_stream_t stream) {
+  loss_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(acc, out, kind, gamma);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_mt_sumsq(const crd_opt_tensor* table, const crd_opt_chunk* chunks, int nchunks, float* sumsq,
+                            crd_stream_t stream) {
+  if (nchunks == 0) return 0;
+  mt_sumsq_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(table, chunks, sumsq);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_diffgradnorm_update(const crd_opt_tensor* table, const crd_opt_chunk* chunks, int nchunks,
+                                       const float* sumsq, const float* egn_in, float* egn_out, float step_size,
+                                       float beta1, float beta2, float eps, crd_stream_t stream) {
+  if (nchunks == 0) return 0;
+  diffgradnorm_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(table, chunks, sumsq, egn_in, egn_out, step_size,
+                                                                 beta1, beta2, eps);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,716 @@
+"""Forward / backward programs of the CamRaDepth hot path on the C-ABI kernels.
+
+The engine is a hand-scheduled tape: `forward` launches the kernels of the encoder
+(simplified_attention.py:265-306) and decoder (CamRaDepth.py:99-170) in stream order and records
+what backward needs; `backward` replays the reverse program and fills one flat fp32 gradient
+buffer (views per parameter, reference parameter order) so data-parallel all-reduce works on
+contiguous buckets.  torch is used only for device memory, the RNG of the stochastic masks and
+stream handles.
+
+Data layout in HBM (bf16 mode; fp32 mode stores everything as fp32):
+  activations NHWC bf16, channel counts padded to multiples of 8 with zero channels;
+  the encoder residual stream, GroupNorm statistics and parameter gradients are fp32;
+  each decoder ShortResBlock owns ONE concat buffer [up(src) | skip | o1(96) | o2(64)] that the
+  producers write slice-wise (no torch.cat copies; utils.py:127-135,249-257).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+from .spec import MID, DROP_PATH_RATE, DROPOUT2D_P
+
+# bumped by optimizers that update parameters through raw pointers (no torch version bump)
+WEIGHT_EPOCH = [0]
+
+
+def bump_weight_epoch():
+    WEIGHT_EPOCH[0] += 1
+
+
+def r8(c):
+    return (c + 7) // 8 * 8
+
+
+class ZeroArena:
+    """Bump allocator over one zero-filled fp32 buffer (one memset per pass instead of hundreds)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+        self.off = 0
+        self.need = 0
+
+    def reset(self):
+        cap = 0 if self.buf is None else self.buf.numel()
+        if self.need > cap:
+            self.buf = torch.empty(int(self.need * 1.1) + 1024, dtype=torch.float32, device=self.device)
+        if self.buf is not None:
+            self.buf.zero_()
+        self.off = 0
+        self.need = 0
+
+    def take(self, *shape):
+        n = 1
+        for s in shape:
+            n *= s
+        n_al = (n + 63) // 64 * 64
+        self.need += n_al
+        if self.buf is not None and self.off + n_al <= self.buf.numel():
+            t = self.buf[self.off:self.off + n].view(*shape)
+            self.off += n_al
+            return t
+        return torch.zeros(*shape, dtype=torch.float32, device=self.device)
+
+
+class Engine:
+    def __init__(self, model, cfg, precision="bf16"):
+        self.model = model
+        self.cfg = cfg
+        self.precision = precision
+        self.tdtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.P = dict(model.named_parameters())
+        self.names = list(self.P.keys())
+        self.device = None
+        self._packs = {}
+        self._maps = {}
+        self.use_tc = False
+        self._build_layers()
+        self.fwd_arena = None
+        self.bwd_arena = None
+
+    # ------------------------------------------------------------------ layer table
+    def _build_layers(self):
+        cfg = self.cfg
+        L = {}
+
+        def add(name, k, stride, pad, cmap=None, cin_p=None):
+            shp = self.P[name].shape
+            cout, cin = shp[0], shp[1]
+            cin_p = r8(cin) if cin_p is None else cin_p
+            L[name] = dict(k=k, stride=stride, pad=pad, cmap=cmap, cin=cin, cin_p=cin_p, cout=cout,
+                           cout_p=r8(cout), taps=k * k)
+
+        pe_k, pe_s = (7, 3, 3, 3), (4, 2, 2, 2)
+        for s in range(4):
+            add(f"dest_encoder.patch_embed{s + 1}.proj.weight", pe_k[s], pe_s[s], pe_k[s] // 2)
+            for i in range(cfg.depths[s]):
+                p = f"dest_encoder.block{s + 1}.{i}"
+                add(p + ".attn.q.weight", 1, 1, 0)
+                add(p + ".attn.k.weight", 1, 1, 0)
+                if cfg.sr[s] > 1:
+                    add(p + ".attn.sr.weight", cfg.sr[s], cfg.sr[s], 0)
+                add(p + ".mlp1.fc1.weight", 1, 1, 0)
+                add(p + ".mlp1.fc2.weight", 1, 1, 0)
+        for j in range(4):
+            add(f"from_encoder_{j + 1}.model.0.weight", 1, 1, 0)
+
+        def short_res(prefix, cx):
+            cxp = r8(cx)
+            for li, extra in enumerate((0, 96, 160)):
+                cin = cx + extra
+                cmap = None if cx == cxp else [c if c < cx else cxp + (c - cx) for c in range(cin)]
+                add(f"{prefix}.conv.layers.{li}.model.0.weight", 3, 1, 1, cmap, cxp + extra)
+
+        d = cfg.dims
+        self.dec_cx = {"depth_upsample.0": d[3] + d[2], "depth_upsample.1": MID + d[1],
+                       "depth_upsample.2": MID + d[0], "depth_upsample.3": MID + 1,
+                       "depth_upsample.4": MID + 1 + cfg.cin}
+        if cfg.sup or cfg.unsup:
+            self.dec_cx["seg_upsample.0"] = MID + 1
+            self.dec_cx["seg_upsample.1"] = MID + 1 + cfg.cin
+        for k, cx in self.dec_cx.items():
+            short_res(k, cx)
+        add("depth_activation_3.conv_1.weight", 3, 1, 1)
+        for n in ("depth_activation_4", "depth_activation_5"):
+            if cfg.nseg:
+                cmap = list(range(MID)) + [MID + 1 + j for j in range(cfg.nseg)]
+                add(n + ".conv_1.weight", 3, 1, 1, cmap, r8(MID + 1 + cfg.nseg))
+            else:
+                add(n + ".conv_1.weight", 3, 1, 1)
+        for n in ("depth_activation_3", "depth_activation_4", "depth_activation_5"):
+            add(n + ".conv_2.weight", 3, 1, 1)
+        if cfg.sup:
+            add("seg_conv_stage_4.weight", 3, 1, 1)
+            add("seg_conv_final.weight", 3, 1, 1)
+        if cfg.unsup:
+            add("unsup_stage_4.weight", 3, 1, 1)
+            add("unsup_final.weight", 3, 1, 1)
+        self.L = L
+
+    # ------------------------------------------------------------------ small helpers
+    def _empty(self, *shape, dtype=None):
+        return torch.empty(*shape, dtype=self.tdtype if dtype is None else dtype, device=self.device)
+
+    def _zeros(self, *shape, dtype=None):
+        return torch.zeros(*shape, dtype=self.tdtype if dtype is None else dtype, device=self.device)
+
+    def _cmap(self, name):
+        cm = self.L[name]["cmap"]
+        if cm is None:
+            return None
+        t = self._maps.get(name)
+        if t is None or t.device != self.device:
+            t = torch.tensor(cm, dtype=torch.int32, device=self.device)
+            self._maps[name] = t
+        return t
+
+    def wpack(self, name, mode, dtype=None):
+        """Packed K-major copy of a conv weight (mode 0: forward / wgrad layout, 1: dgrad layout)."""
+        dtype = self.tdtype if dtype is None else dtype
+        p = self.P[name]
+        L = self.L[name]
+        if mode == 0 and dtype == torch.float32 and L["taps"] == 1 and L["cmap"] is None and L["cin_p"] == L["cin"]:
+            return p.detach()
+        key = (name, mode, dtype)
+        ver = (p._version, p.data_ptr(), WEIGHT_EPOCH[0])
+        ent = self._packs.get(key)
+        if ent is not None and ent[1] == ver:
+            return ent[0]
+        if ent is not None and ent[0].device == self.device:
+            dst = ent[0]
+        elif mode == 0:
+            dst = torch.zeros(L["cout"], L["taps"] * L["cin_p"], dtype=dtype, device=self.device)
+        else:
+            dst = torch.zeros(L["cin_p"], L["taps"] * L["cout_p"], dtype=dtype, device=self.device)
+        ops.weight_pack(p.detach(), dst, self._cmap(name), L["cout"], L["cin"], L["taps"], L["cin_p"], L["cout_p"],
+                        mode)
+        self._packs[key] = (dst, ver)
+        return dst
+
+    def _tc_ok(self, L, x, y_or_dy):
+        return False
+
+    def conv(self, x, name, y, bias=None, act=0, accumulate=0, out_nchw=0):
+        L = self.L[name]
+        w = self.wpack(name, 0)
+        d = ops.make_desc(x, y, L["cin_p"], L["cout"], L["k"], L["k"], L["stride"], L["pad"], 0, act, accumulate,
+                          out_nchw)
+        b = None if bias is None else self.P[bias].detach()
+        ops.conv_fwd(d, x, w, b, y, use_tc=self.use_tc and self._tc_ok(L, x, y))
+
+    def conv_dgrad(self, dy, name, dx, accumulate):
+        L = self.L[name]
+        w = self.wpack(name, 1)
+        d = ops.make_desc(dy, dx, L["cout_p"], L["cin_p"], L["k"], L["k"], L["stride"], L["pad"], 1, 0,
+                          int(accumulate), 0)
+        ops.conv_fwd(d, dy, w, None, dx, use_tc=self.use_tc and self._tc_ok(L, dy, dx))
+
+    def conv_wgrad(self, x, dy, name, bias=None):
+        L = self.L[name]
+        direct = L["taps"] == 1 and L["cmap"] is None and L["cin_p"] == L["cin"]
+        g = self.pg[name]
+        dwp = g.view(L["cout"], L["cin"]) if direct else self.bwd_arena.take(L["cout"], L["taps"] * L["cin_p"])
+        d = ops.make_desc(x, dy, L["cin_p"], L["cout"], L["k"], L["k"], L["stride"], L["pad"], 0, 0, 0, 0)
+        ops.conv_wgrad(d, x, dy, dwp, use_tc=self.use_tc and self._tc_ok(L, x, dy))
+        if not direct:
+            ops.weight_unpack_grad(dwp, g, self._cmap(name), L["cout"], L["cin"], L["taps"], L["cin_p"], False)
+        if bias is not None:
+            ops.col_sum(dy, self.pg[bias], L["cout"])
+
+    def gn_fwd(self, x, prefix, G, want_xbar=False):
+        B, N, C = ops._bnc(x)
+        sums = self.fwd_arena.take(B, C, 2)
+        ops.chan_stats(x, sums)
+        ab = self._empty(B, C, 2, dtype=torch.float32)
+        mr = self._empty(B, G, 2, dtype=torch.float32)
+        xbar = self._empty(B, C, dtype=torch.float32) if want_xbar else None
+        ops.gn_finalize(sums, self.P[prefix + ".weight"].detach(), self.P[prefix + ".bias"].detach(), ab, mr, xbar,
+                        B, C, G, N)
+        return ab, mr, xbar
+
+    def gn_bwd(self, dy, x, ab, mr, prefix, G, act, post, addbc, dx, accumulate):
+        B, N, C = ops._bnc(x)
+        pq = self.bwd_arena.take(B, C, 2)
+        ops.gnact_bwd_reduce(dy, x, ab, post, addbc, act, pq)
+        coef = self._empty(B, C, 3, dtype=torch.float32)
+        ops.gn_bwd_finalize(pq, mr, self.P[prefix + ".weight"].detach(), coef, self.pg[prefix + ".weight"],
+                            self.pg[prefix + ".bias"], B, C, G, N)
+        ops.gnact_bwd_apply(dy, x, ab, post, addbc, act, coef, dx, accumulate)
+
+    # ------------------------------------------------------------------ masks
+    def make_masks(self, B):
+        cfg = self.cfg
+        nb = sum(cfg.depths)
+        rates = torch.linspace(0, DROP_PATH_RATE, nb).tolist()     # simplified_attention.py:214
+        dps = []
+        for r in rates:
+            if r == 0.0:
+                dps.append(None)                                    # Identity (:123)
+            else:
+                keep = 1.0 - r
+                dps.append((torch.rand(B, device=self.device) < keep).float() / keep)
+        d2s = [(torch.rand(B, MID, device=self.device) >= DROPOUT2D_P).float() / (1 - DROPOUT2D_P)
+               for _ in range(cfg.n_dropout_sites)]
+        return dps, d2s
+
+    # ------------------------------------------------------------------ encoder forward
+    def pe_fwd(self, s, xin, save):
+        cfg = self.cfg
+        name = f"dest_encoder.patch_embed{s + 1}"
+        L = self.L[name + ".proj.weight"]
+        B, H, W, _ = xin.shape
+        Ho = (H + 2 * L["pad"] - L["k"]) // L["stride"] + 1
+        Wo = (W + 2 * L["pad"] - L["k"]) // L["stride"] + 1
+        C = cfg.dims[s]
+        y = self._empty(B, Ho, Wo, C)
+        self.conv(xin, name + ".proj.weight", y, bias=name + ".proj.bias")
+        ab, mr, _ = self.gn_fwd(y, name + ".norm", C // cfg.gn_div)
+        x0 = self._empty(B, Ho, Wo, C, dtype=torch.float32)
+        ops.affine_act(y, x0, ab, None, ops.ACT_NONE)
+        rec = dict(xin=xin, y=y, ab=ab, mr=mr) if save else None
+        return x0, rec
+
+    def pe_bwd(self, s, rec, dx, dxin, accumulate):
+        cfg = self.cfg
+        name = f"dest_encoder.patch_embed{s + 1}"
+        C = cfg.dims[s]
+        dy = self._empty(*rec["y"].shape)
+        self.gn_bwd(dx, rec["y"], rec["ab"], rec["mr"], name + ".norm", C // cfg.gn_div, ops.ACT_NONE, None, None,
+                    dy, False)
+        self.conv_wgrad(rec["xin"], dy, name + ".proj.weight", bias=name + ".proj.bias")
+        if dxin is not None:
+            self.conv_dgrad(dy, name + ".proj.weight", dxin, accumulate)
+
+    def block_fwd(self, s, i, x, dp, save):
+        cfg = self.cfg
+        p = f"dest_encoder.block{s + 1}.{i}"
+        B, H, W, C = x.shape
+        N = H * W
+        heads, sr = cfg.heads[s], cfg.sr[s]
+        rC = int(C * cfg.ff[s])
+        G = C // cfg.gn_div
+        f32 = torch.float32
+        ab1, mr1, xbar1 = self.gn_fwd(x, p + ".norm1", G, want_xbar=True)
+        x1 = self._empty(B, H, W, C)
+        ops.affine_act(x, x1, ab1, None, ops.ACT_NONE)
+        q = self._empty(B, H, W, C)
+        self.conv(x1, p + ".attn.q.weight", q, bias=p + ".attn.q.bias")
+        rec = {}
+        if sr > 1:
+            Hs, Ws = H // sr, W // sr
+            xs = self._empty(B, Hs, Ws, C)
+            self.conv(x1, p + ".attn.sr.weight", xs, bias=p + ".attn.sr.bias")
+            ab_s, mr_s, _ = self.gn_fwd(xs, p + ".attn.norm", G)
+            xsn = self._empty(B, Hs, Ws, C)
+            ops.affine_act(xs, xsn, ab_s, None, ops.ACT_NONE)
+            kin = xsn
+            rec.update(xs=xs, ab_s=ab_s, mr_s=mr_s, xsn=xsn)
+        else:
+            Hs, Ws = H, W
+            kin = x1
+        M = Hs * Ws
+        k = self._empty(B, Hs, Ws, C)
+        self.conv(kin, p + ".attn.k.weight", k, bias=p + ".attn.k.bias")
+        sc = self._empty(B, N, dtype=f32)
+        idx = torch.empty(B, heads, N, dtype=torch.int16, device=self.device)
+        scale = float((C // heads) ** -0.5)
+        ops.attn_qkmax_fwd(q.view(B, N, C), k.view(B, M, C), sc, idx, heads, scale)
+        pv = self._empty(B, C, dtype=f32)
+        ops.attn_pv_fwd(xbar1, self.P[p + ".attn.proj.weight"].detach(), pv)
+        x_mid = self._empty(B, H, W, C, dtype=f32)
+        ops.attn_out_residual(x.view(B, N, C), pv, sc, self.P[p + ".attn.proj.bias"].detach(), dp,
+                              x_mid.view(B, N, C))
+        # Mix-FFN
+        ab2, mr2, _ = self.gn_fwd(x_mid, p + ".norm2", G)
+        x2 = self._empty(B, H, W, C)
+        ops.affine_act(x_mid, x2, ab2, None, ops.ACT_NONE)
+        h1 = self._empty(B, H, W, rC)
+        self.conv(x2, p + ".mlp1.fc1.weight", h1, bias=p + ".mlp1.fc1.bias")
+        ab_m1, mr_m1, _ = self.gn_fwd(h1, p + ".mlp1.norm1", rC // cfg.gn_div)
+        h2 = self._empty(B, H, W, rC)
+        ops.dwconv_fwd(h1, ab_m1, self.P[p + ".mlp1.dwconv.dwconv.weight"].detach(),
+                       self.P[p + ".mlp1.dwconv.dwconv.bias"].detach(), h2)
+        ab_m2, mr_m2, _ = self.gn_fwd(h2, p + ".mlp1.norm2", G)
+        h3 = self._empty(B, H, W, rC)
+        ops.affine_act(h2, h3, ab_m2, None, ops.ACT_GELU)
+        y2 = self._empty(B, H, W, C)
+        self.conv(h3, p + ".mlp1.fc2.weight", y2, bias=p + ".mlp1.fc2.bias")
+        x_out = self._empty(B, H, W, C, dtype=f32)
+        ops.residual_add(x_mid.view(B, N, C), y2.view(B, N, C), dp, x_out.view(B, N, C))
+        if not save:
+            return x_out, None
+        rec.update(x=x, ab1=ab1, mr1=mr1, xbar1=xbar1, x1=x1, q=q, k=k, sc=sc, idx=idx, pv=pv, x_mid=x_mid,
+                   ab2=ab2, mr2=mr2, x2=x2, h1=h1, ab_m1=ab_m1, mr_m1=mr_m1, h2=h2, ab_m2=ab_m2, mr_m2=mr_m2,
+                   h3=h3, dp=dp, M=M, scale=scale)
+        return x_out, rec
+
+    def block_bwd(self, s, i, rec, dx):
+        """dx: fp32 grad wrt the block output; updated IN PLACE to the grad wrt the block input."""
+        cfg = self.cfg
+        p = f"dest_encoder.block{s + 1}.{i}"
+        B, H, W, C = dx.shape
+        N = H * W
+        heads, sr = cfg.heads[s], cfg.sr[s]
+        rC = int(C * cfg.ff[s])
+        G = C // cfg.gn_div
+        f32 = torch.float32
+        dp = rec["dp"]
+        # ---- Mix-FFN branch
+        dy2 = self._empty(B, H, W, C)
+        ops.scale_cast(dx, dp, dy2)
+        self.conv_wgrad(rec["h3"], dy2, p + ".mlp1.fc2.weight", bias=p + ".mlp1.fc2.bias")
+        dh3 = self._empty(B, H, W, rC)
+        self.conv_dgrad(dy2, p + ".mlp1.fc2.weight", dh3, False)
+        dh2 = self._empty(B, H, W, rC)
+        self.gn_bwd(dh3, rec["h2"], rec["ab_m2"], rec["mr_m2"], p + ".mlp1.norm2", G, ops.ACT_GELU, None, None, dh2,
+                    False)
+        del dh3
+        ops.dwconv_bwd_weight(dh2, rec["h1"], rec["ab_m1"], self.pg[p + ".mlp1.dwconv.dwconv.weight"],
+                              self.pg[p + ".mlp1.dwconv.dwconv.bias"])
+        dh1n = self._empty(B, H, W, rC)
+        ops.dwconv_bwd_input(dh2, self.P[p + ".mlp1.dwconv.dwconv.weight"].detach(), dh1n)
+        dh1 = dh2   # reuse
+        self.gn_bwd(dh1n, rec["h1"], rec["ab_m1"], rec["mr_m1"], p + ".mlp1.norm1", rC // cfg.gn_div, ops.ACT_NONE,
+                    None, None, dh1, False)
+        del dh1n
+        self.conv_wgrad(rec["x2"], dh1, p + ".mlp1.fc1.weight", bias=p + ".mlp1.fc1.bias")
+        dx2 = dy2   # reuse
+        self.conv_dgrad(dh1, p + ".mlp1.fc1.weight", dx2, False)
+        self.gn_bwd(dx2, rec["x_mid"], rec["ab2"], rec["mr2"], p + ".norm2", G, ops.ACT_NONE, None, None, dx, True)
+        # ---- attention branch (dx is now the grad wrt x_mid)
+        ds = self._empty(B, N, dtype=f32)
+        dpv = self._empty(B, C, dtype=f32)
+        tmp = self._empty(B, C, 2, dtype=f32)
+        ops.attn_out_bwd(dx.view(B, N, C), rec["pv"], rec["sc"], dp, ds, dpv, self.pg[p + ".attn.proj.bias"], tmp)
+        dxbar = self._empty(B, C, dtype=f32)
+        ops.attn_pv_bwd(dpv, rec["xbar1"], self.P[p + ".attn.proj.weight"].detach(),
+                        self.pg[p + ".attn.proj.weight"], dxbar, 1.0 / N)
+        M = rec["M"]
+        dq = self._empty(B, H, W, C)
+        dk32 = self.bwd_arena.take(B, M, C)
+        ops.attn_qkmax_bwd(ds, rec["q"].view(B, N, C), rec["k"].view(B, M, C), rec["idx"], dq.view(B, N, C), dk32,
+                           heads, rec["scale"])
+        self.conv_wgrad(rec["x1"], dq, p + ".attn.q.weight", bias=p + ".attn.q.bias")
+        dx1 = dx2   # reuse (T, B,H,W,C)
+        self.conv_dgrad(dq, p + ".attn.q.weight", dx1, False)
+        kshape = rec["k"].shape
+        dk = self._empty(*kshape)
+        ops.scale_cast(dk32.view(*kshape), None, dk)
+        if sr > 1:
+            self.conv_wgrad(rec["xsn"], dk, p + ".attn.k.weight", bias=p + ".attn.k.bias")
+            dxsn = self._empty(*kshape)
+            self.conv_dgrad(dk, p + ".attn.k.weight", dxsn, False)
+            dxs = dk   # reuse
+            self.gn_bwd(dxsn, rec["xs"], rec["ab_s"], rec["mr_s"], p + ".attn.norm", G, ops.ACT_NONE, None, None,
+                        dxs, False)
+            self.conv_wgrad(rec["x1"], dxs, p + ".attn.sr.weight", bias=p + ".attn.sr.bias")
+            self.conv_dgrad(dxs, p + ".attn.sr.weight", dx1, True)
+        else:
+            self.conv_wgrad(rec["x1"], dk, p + ".attn.k.weight", bias=p + ".attn.k.bias")
+            self.conv_dgrad(dk, p + ".attn.k.weight", dx1, True)
+        self.gn_bwd(dx1, rec["x"], rec["ab1"], rec["mr1"], p + ".norm1", G, ops.ACT_NONE, None, dxbar, dx, True)
+
+    # ------------------------------------------------------------------ decoder pieces
+    def convlayer_fwd(self, x, prefix, dest, post, save, act=ops.ACT_GELU):
+        """ConvLayer (utils.py:223-228): conv(no bias) -> GN(Cout/16) -> GELU, output written into `dest`."""
+        name = prefix + ".model.0.weight"
+        L = self.L[name]
+        B, H, W, _ = x.shape
+        y = self._empty(B, H, W, L["cout"])
+        self.conv(x, name, y)
+        ab, mr, _ = self.gn_fwd(y, prefix + ".model.1", L["cout"] // self.cfg.gn_div)
+        ops.affine_act(y, dest, ab, post, act)
+        return dict(x=x, y=y, ab=ab, mr=mr, post=post) if save else None
+
+    def convlayer_bwd(self, prefix, rec, ddest, dx, accumulate):
+        name = prefix + ".model.0.weight"
+        L = self.L[name]
+        dy = self._empty(*rec["y"].shape)
+        self.gn_bwd(ddest, rec["y"], rec["ab"], rec["mr"], prefix + ".model.1", L["cout"] // self.cfg.gn_div,
+                    ops.ACT_GELU, rec["post"], None, dy, False)
+        self.conv_wgrad(rec["x"], dy, name)
+        if dx is not None:
+            self.conv_dgrad(dy, name, dx, accumulate)
+
+    def dec_fwd(self, prefix, src, skip_fn, dest, post, save):
+        """Decoder (utils.py:249-257): bicubic x2 -> cat(skip) -> ShortResBlock (utils.py:127-135).
+
+        src: NHWC buffer whose channels (all, zero padded) are upsampled; skip_fn(view) writes the
+        skip tensor into its slice of the concat buffer; dest: NHWC view receiving the 128 outputs.
+        """
+        cx = self.dec_cx[prefix]
+        cxp = r8(cx)
+        B, h, w, cs = src.shape
+        ct = cxp + 160
+        cat = self._empty(B, 2 * h, 2 * w, ct)
+        ops.bicubic2x_fwd(src, cat[..., :cs])
+        if skip_fn is not None:
+            skip_fn(cat)
+        recs = []
+        recs.append(self.convlayer_fwd(cat[..., :cxp], f"{prefix}.conv.layers.0", cat[..., cxp:cxp + 96], None, save))
+        recs.append(self.convlayer_fwd(cat[..., :cxp + 96], f"{prefix}.conv.layers.1", cat[..., cxp + 96:ct], None,
+                                       save))
+        recs.append(self.convlayer_fwd(cat, f"{prefix}.conv.layers.2", dest, post, save))
+        return dict(cat=cat, recs=recs, cs=cs, cxp=cxp) if save else None
+
+    def dec_bwd(self, prefix, rec, ddest, dsrc, src_accumulate):
+        """Returns the grad of the concat buffer (callers slice the skip part out of it)."""
+        cat, recs, cs, cxp = rec["cat"], rec["recs"], rec["cs"], rec["cxp"]
+        ct = cxp + 160
+        dcat = self._empty(*cat.shape)
+        self.convlayer_bwd(f"{prefix}.conv.layers.2", recs[2], ddest, dcat, False)
+        self.convlayer_bwd(f"{prefix}.conv.layers.1", recs[1], dcat[..., cxp + 96:ct], dcat[..., :cxp + 96], True)
+        self.convlayer_bwd(f"{prefix}.conv.layers.0", recs[0], dcat[..., cxp:cxp + 96], dcat[..., :cxp], True)
+        if dsrc is not None:
+            ops.bicubic2x_bwd(dcat[..., :cs], dsrc, src_accumulate)
+        return dcat
+
+    def da_fwd(self, name, F, save):
+        """Depth_Activation (utils.py:285-289): conv3x3(+bias) -> sigmoid -> conv3x3(32->1, +bias)."""
+        L = self.L[name + ".conv_1.weight"]
+        B, H, W, _ = F.shape
+        sg = self._empty(B, H, W, 32)
+        self.conv(F[..., :L["cin_p"]], name + ".conv_1.weight", sg, bias=name + ".conv_1.bias", act=ops.ACT_SIGMOID)
+        w2 = self.wpack(name + ".conv_2.weight", 0, dtype=torch.float32)
+        depth = self._empty(B, 1, H, W, dtype=torch.float32)
+        ops.conv3x3_c1_fwd(sg, w2, self.P[name + ".conv_2.bias"].detach(), depth)
+        return depth, (dict(F=F, sg=sg) if save else None)
+
+    def da_bwd(self, name, rec, ddepth, dF, accumulate):
+        L = self.L[name + ".conv_1.weight"]
+        sg, F = rec["sg"], rec["F"]
+        w2 = self.wpack(name + ".conv_2.weight", 0, dtype=torch.float32)
+        dsg = self._empty(*sg.shape)
+        dw2 = self.bwd_arena.take(1, 9 * 32)
+        ops.conv3x3_c1_bwd(ddepth, sg, w2, dsg, dw2, self.pg[name + ".conv_2.bias"])
+        ops.weight_unpack_grad(dw2, self.pg[name + ".conv_2.weight"], None, 1, 32, 9, 32, False)
+        dpre = self._empty(*sg.shape)
+        ops.sigmoid_bwd(dsg, sg, dpre)
+        self.conv_wgrad(F[..., :L["cin_p"]], dpre, name + ".conv_1.weight", bias=name + ".conv_1.bias")
+        self.conv_dgrad(dpre, name + ".conv_1.weight", dF[..., :L["cin_p"]], accumulate)
+
+    def seg_logits(self, F, name, out_dtype):
+        """3x3 conv 128 -> ncls (+bias) (CamRaDepth.py:129,133,155,159); NHWC logits padded to 24 channels."""
+        L = self.L[name + ".weight"]
+        B, H, W, _ = F.shape
+        lg = self._zeros(B, H, W, L["cout_p"], dtype=out_dtype)
+        self.conv(F[..., :MID], name + ".weight", lg, bias=name + ".bias")
+        return lg
+
+    # ------------------------------------------------------------------ whole forward
+    def forward(self, x, train, masks=None, save=True):
+        cfg = self.cfg
+        if not x.is_cuda:
+            raise RuntimeError("camradepth_b200 runs on CUDA devices only (no CPU fallback by design)")
+        if self.device != x.device:
+            self.device = x.device
+            self.fwd_arena = ZeroArena(self.device)
+            self.bwd_arena = ZeroArena(self.device)
+        B, cin, H, W = x.shape
+        if cin != cfg.cin:
+            raise RuntimeError(f"expected {cfg.cin} input channels, got {cin}")
+        if H % 32 or W % 32:
+            raise RuntimeError(f"Sizes of tensors must match: H and W must be multiples of 32, got {H}x{W}")
+        x = x.detach().contiguous().float()
+        self.fwd_arena.reset()
+        if train:
+            dps, d2s = masks if masks is not None else self.make_masks(B)
+        else:
+            dps, d2s = [None] * sum(cfg.depths), [None] * cfg.n_dropout_sites
+        S = dict(B=B, H=H, W=W)
+        f32 = torch.float32
+
+        # ---- encoder (SimplifiedTransformer.forward_features, simplified_attention.py:265-306)
+        X0 = self._zeros(B, H, W, r8(cin))
+        ops.nchw_to_nhwc(x, X0)
+        cur = X0
+        stage_T, pe_recs, blk_recs = [], [], []
+        bi = 0
+        for s in range(4):
+            xr, prec = self.pe_fwd(s, cur, save)
+            pe_recs.append(prec)
+            brs = []
+            for i in range(cfg.depths[s]):
+                dp = dps[bi]
+                dp = None if dp is None else dp.to(self.device, f32).contiguous()
+                xr, brec = self.block_fwd(s, i, xr, dp, save)
+                brs.append(brec)
+                bi += 1
+            blk_recs.append(brs)
+            st = self._empty(*xr.shape)
+            ops.scale_cast(xr, None, st)
+            stage_T.append(st)
+            cur = st
+        S.update(pe=pe_recs, blk=blk_recs, stage_T=stage_T)
+
+        # ---- decoder (CamRaDepth.dest_decoder, CamRaDepth.py:99-170)
+        d2 = [None if m is None else m.to(self.device, f32).contiguous() for m in d2s]
+        h0, w0 = H // 32, W // 32
+        E1 = self._empty(B, h0, w0, cfg.dims[3])
+        S["fe1"] = self.convlayer_fwd(stage_T[3], "from_encoder_1", E1, None, save)
+        fe = {}
+
+        def skip_from(j, stage, c0):
+            def fn(cat):
+                C = stage.shape[-1]
+                fe[j] = self.convlayer_fwd(stage, f"from_encoder_{j}", cat[..., c0:c0 + C], None, save)
+            return fn
+
+        F1 = self._empty(B, 2 * h0, 2 * w0, MID)
+        S["D0"] = self.dec_fwd("depth_upsample.0", E1, skip_from(2, stage_T[2], cfg.dims[3]), F1, d2[0], save)
+        F2 = self._empty(B, 4 * h0, 4 * w0, MID)
+        S["D1"] = self.dec_fwd("depth_upsample.1", F1, skip_from(3, stage_T[1], MID), F2, d2[1], save)
+        FW = r8(MID + 1 + cfg.nseg)                    # [feat 128 | depth | seg maps | zero pad]
+        F3 = self._zeros(B, 8 * h0, 8 * w0, FW)
+        S["D2"] = self.dec_fwd("depth_upsample.2", F2, skip_from(4, stage_T[0], MID), F3[..., :MID], d2[2], save)
+        S["fe"] = fe
+        inter3, S["DA3"] = self.da_fwd("depth_activation_3", F3, save)
+        ops.nchw_to_nhwc(inter3, F3[..., MID:MID + 1])
+        F4 = self._zeros(B, 16 * h0, 16 * w0, FW)
+        S["D3"] = self.dec_fwd("depth_upsample.3", F3, None, F4[..., :MID], d2[3], save)
+        seg = cfg.sup or cfg.unsup
+        FS4 = None
+        if seg:
+            FS4 = self._zeros(B, 16 * h0, 16 * w0, FW)
+            S["S0"] = self.dec_fwd("seg_upsample.0", F3, None, FS4[..., :MID], d2[4], save)
+            if cfg.sup:
+                lg = self.seg_logits(FS4, "seg_conv_stage_4", self.tdtype)
+                ops.argmax_map(lg, cfg.num_classes, FS4[..., MID:MID + 1], None)
+                ops.argmax_map(lg, cfg.num_classes, F4[..., MID + 1:MID + 2], None)
+            if cfg.unsup:
+                lg = self.seg_logits(FS4, "unsup_stage_4", self.tdtype)
+                j = MID + 1 + int(cfg.sup)
+                ops.argmax_map(lg, 19, F4[..., j:j + 1], None)
+                if not cfg.sup:
+                    ops.argmax_map(lg, 19, FS4[..., MID:MID + 1], None)
+        inter4, S["DA4"] = self.da_fwd("depth_activation_4", F4, save)
+        ops.nchw_to_nhwc(inter4, F4[..., MID:MID + 1])
+
+        def skip_input(cat):
+            ops.nchw_to_nhwc(x, cat[..., MID + 1:MID + 1 + cin])
+
+        F5 = self._zeros(B, H, W, FW)
+        S["D4"] = self.dec_fwd("depth_upsample.4", F4, skip_input, F5[..., :MID], d2[5 if seg else 4], save)
+        final_seg = unsup_map = None
+        if seg:
+            FS5 = self._empty(B, H, W, MID)
+            S["S1"] = self.dec_fwd("seg_upsample.1", FS4, skip_input, FS5, d2[6], save)
+            S["FS5"] = FS5
+            if cfg.sup:
+                lg = self.seg_logits(FS5, "seg_conv_final", f32)
+                final_seg = self._empty(B, cfg.num_classes, H, W, dtype=f32)
+                ops.nhwc_to_nchw(lg, final_seg)
+                ops.argmax_map(lg, cfg.num_classes, F5[..., MID + 1:MID + 2], None)
+            if cfg.unsup:
+                lg = self.seg_logits(FS5, "unsup_final", self.tdtype)
+                unsup_map = self._empty(B, 1, H, W, dtype=f32)
+                j = MID + 1 + int(cfg.sup)
+                ops.argmax_map(lg, 19, F5[..., j:j + 1], unsup_map)
+        final_depth, S["DA5"] = self.da_fwd("depth_activation_5", F5, save)
+        outs = dict(final_depth=final_depth, inter3=inter3, inter4=inter4, final_seg=final_seg, unsup_map=unsup_map)
+        return outs, (S if save else None)
+
+    # ------------------------------------------------------------------ whole backward
+    def backward(self, S, g_final, g3, g4, g_seg, flat_grad=None, on_bucket=None):
+        """-> dict name -> fp32 grad view (params without a gradient path are absent)."""
+        cfg = self.cfg
+        B, H, W = S["B"], S["H"], S["W"]
+        f32 = torch.float32
+        self.bwd_arena.reset()
+        sizes = [self.P[n].numel() for n in self.names]
+        total = sum(sizes)
+        flat = torch.zeros(total, dtype=f32, device=self.device) if flat_grad is None else flat_grad
+        self.pg = {}
+        off = 0
+        self.pg_offsets = {}
+        for n, sz in zip(self.names, sizes):
+            self.pg[n] = flat[off:off + sz].view(self.P[n].shape)
+            self.pg_offsets[n] = (off, sz)
+            off += sz
+        self.flat_grad = flat
+        h0, w0 = H // 32, W // 32
+        seg = cfg.sup or cfg.unsup
+        FW = r8(MID + 1 + cfg.nseg)
+
+        def gz(g, shape):
+            if g is None:
+                return torch.zeros(*shape, dtype=f32, device=self.device)
+            return g.detach().contiguous().float()
+
+        # ---- heads at full resolution
+        dF5 = self._zeros(B, H, W, FW)
+        self.da_bwd("depth_activation_5", S["DA5"], gz(g_final, (B, 1, H, W)), dF5, False)
+        sup_grad = cfg.sup and g_seg is not None
+        dFS4 = None
+        if sup_grad:
+            dlg = self._zeros(B, H, W, r8(cfg.num_classes))
+            ops.nchw_to_nhwc(gz(g_seg, ()), dlg)
+            FS5 = S["FS5"]
+            self.conv_wgrad(FS5, dlg, "seg_conv_final.weight", bias="seg_conv_final.bias")
+            dFS5 = self._empty(B, H, W, MID)
+            self.conv_dgrad(dlg, "seg_conv_final.weight", dFS5, False)
+            dFS4 = self._empty(B, 16 * h0, 16 * w0, FW)
+            self.dec_bwd("seg_upsample.1", S["S1"], dFS5, dFS4, False)
+            del dFS5, dlg
+        dF4 = self._empty(B, 16 * h0, 16 * w0, FW)
+        self.dec_bwd("depth_upsample.4", S["D4"], dF5[..., :MID], dF4, False)
+        del dF5
+        # inter_depth_4 receives grad from the loss and from the upsampled concat (CamRaDepth.py:144)
+        d4 = gz(g4, (B, 1, 16 * h0, 16 * w0)).clone() if g4 is not None else self._zeros(B, 1, 16 * h0, 16 * w0, dtype=f32)
+        t4 = self._empty(B, 1, 16 * h0, 16 * w0, dtype=f32)
+        ops.nhwc_to_nchw(dF4[..., MID:MID + 1], t4)
+        ops.add_f32(d4, t4)
+        self.da_bwd("depth_activation_4", S["DA4"], d4, dF4, True)
+        dF3 = self._empty(B, 8 * h0, 8 * w0, FW)
+        acc3 = False
+        if sup_grad:
+            self.dec_bwd("seg_upsample.0", S["S0"], dFS4[..., :MID], dF3, False)
+            acc3 = True
+            del dFS4
+        self.dec_bwd("depth_upsample.3", S["D3"], dF4[..., :MID], dF3, acc3)
+        del dF4
+        d3 = gz(g3, (B, 1, 8 * h0, 8 * w0)).clone() if g3 is not None else self._zeros(B, 1, 8 * h0, 8 * w0, dtype=f32)
+        t3 = self._empty(B, 1, 8 * h0, 8 * w0, dtype=f32)
+        ops.nhwc_to_nchw(dF3[..., MID:MID + 1], t3)
+        ops.add_f32(d3, t3)
+        self.da_bwd("depth_activation_3", S["DA3"], d3, dF3, True)
+        if on_bucket:
+            on_bucket("heads")
+        # ---- pyramid
+        stage_T = S["stage_T"]
+        dstage = [self._empty(*t.shape) for t in stage_T]
+        dF2 = self._empty(B, 4 * h0, 4 * w0, MID)
+        dcat = self.dec_bwd("depth_upsample.2", S["D2"], dF3[..., :MID], dF2, False)
+        self.convlayer_bwd("from_encoder_4", S["fe"][4], dcat[..., MID:MID + cfg.dims[0]], dstage[0], False)
+        del dF3, dcat
+        dF1 = self._empty(B, 2 * h0, 2 * w0, MID)
+        dcat = self.dec_bwd("depth_upsample.1", S["D1"], dF2, dF1, False)
+        self.convlayer_bwd("from_encoder_3", S["fe"][3], dcat[..., MID:MID + cfg.dims[1]], dstage[1], False)
+        del dF2, dcat
+        dE1 = self._empty(B, h0, w0, cfg.dims[3])
+        dcat = self.dec_bwd("depth_upsample.0", S["D0"], dF1, dE1, False)
+        self.convlayer_bwd("from_encoder_2", S["fe"][2], dcat[..., cfg.dims[3]:cfg.dims[3] + cfg.dims[2]], dstage[2],
+                           False)
+        del dF1, dcat
+        self.convlayer_bwd("from_encoder_1", S["fe1"], dE1, dstage[3], False)
+        if on_bucket:
+            on_bucket("decoder")
+        # ---- encoder, last stage first
+        for s in (3, 2, 1, 0):
+            dx = torch.zeros(*stage_T[s].shape, dtype=f32, device=self.device)
+            ops.add_f32(dx, dstage[s])
+            for i in reversed(range(cfg.depths[s])):
+                self.block_bwd(s, i, S["blk"][s][i], dx)
+            self.pe_bwd(s, S["pe"][s], dx, dstage[s - 1] if s > 0 else None, True)
+            if on_bucket:
+                on_bucket(f"stage{s}")
+        grads = dict(self.pg)
+        for n in self.no_grad_names(sup_grad):
+            grads.pop(n, None)
+        self.pg = None
+        return grads
+
+    def no_grad_names(self, sup_grad=True):
+        """Parameters with no gradient path: argmax-fed heads; the whole seg branch if unsupervised."""
+        cfg = self.cfg
+        out = []
+        if cfg.sup:
+            out += ["seg_conv_stage_4.weight", "seg_conv_stage_4.bias"]
+        if cfg.unsup:
+            out += ["unsup_stage_4.weight", "unsup_stage_4.bias", "unsup_final.weight", "unsup_final.bias"]
+        if (cfg.sup or cfg.unsup) and not sup_grad:
+            out += [n for n in self.names if n.startswith("seg_upsample.") or n.startswith("seg_conv_final")]
+        return out

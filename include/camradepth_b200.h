@@ -1,0 +1,205 @@
+/*
+ * camradepth_b200 -- C ABI of the B200 (sm_100a) kernels behind the CamRaDepth hot path.
+ *
+ * The reference (TUMFTM/CamRaDepth) has NO native/FFI layer: every op on the path is an eager
+ * ATen call made from Python.  The boundary a maintainer binds is therefore this
+ * library, loaded with ctypes from the drop-in `CamRaDepth` nn.Module.  Each
+ * entry point names the reference code it replaces (file:line under /root/reference).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless stated; no allocation
+ *     inside the library (workspaces are passed in); all launches go to `stream`.
+ *   - return 0 on success, a cudaError_t (>0) on a launch error, < 0 on an argument error.
+ *   - activations are NHWC ("tokens" (B,N,C) are NHWC with H*W = N); `ld*` = elements between
+ *     consecutive pixels, so a tensor may be a channel slice of a wider concat buffer.  Channel
+ *     counts handed to kernels are multiples of 8 (callers pad with zero channels).
+ *   - dtype codes: CRD_F32 = 0, CRD_BF16 = 1.  Statistics, residual streams, losses, optimizer
+ *     state and parameter gradients are always fp32.
+ */
+#ifndef CAMRADEPTH_B200_H
+#define CAMRADEPTH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* crd_stream_t; /* cudaStream_t */
+
+#define CRD_API __attribute__((visibility("default")))
+
+#define CRD_F32 0
+#define CRD_BF16 1
+#define CRD_ACT_NONE 0
+#define CRD_ACT_GELU 1
+#define CRD_ACT_SIGMOID 2
+
+CRD_API int crd_version(void);
+/* number of kernels launched by this library since load (bench.py "gpu_launches") */
+CRD_API unsigned long long crd_launch_count(void);
+/* 1 if the tcgen05/TMA kernels can run on the current device (sm_100) */
+CRD_API int crd_has_tcgen05(void);
+
+/* ---------------------------------------------------------------- layout (boundary NCHW <-> NHWC)
+ * Replaces nothing in the reference (which is NCHW throughout); this is the price of the drop-in
+ * NCHW fp32 nn.Module surface (CamRaDepth.py:173-176). */
+CRD_API int crd_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int B, int C, int H, int W, int ld_dst,
+                     crd_stream_t stream);
+CRD_API int crd_nhwc_to_nchw(const void* src, int src_dtype, float* dst, int B, int C, int H, int W, int ld_src,
+                     crd_stream_t stream);
+
+/* ---------------------------------------------------------------- convolution as implicit GEMM
+ * y[b,oh,ow,n] = sum_{kh,kw,c} x[b, oh*stride-pad+kh, ow*stride-pad+kw, c] * w[n][(kh*KW+kw)*Cin + c]
+ * (transposed=1: x is read at ((oh+pad-kh)/stride, (ow+pad-kw)/stride) when divisible -- the data
+ * gradient of a strided conv).  Replaces F.conv2d / F.conv1d at simplified_attention.py:35,41,92,
+ * 98,101,108,184,321; utils.py:225,286,288; CamRaDepth.py:129,133,155,159 and their autograd
+ * backward (aten convolution_backward). */
+typedef struct {
+  int B, H, W;          /* tensor being read */
+  int Cin, ldx;         /* channels read (multiple of 8), pixel stride */
+  int Ho, Wo, Cout;     /* tensor being written */
+  int ldy;
+  int KH, KW, stride, pad;
+  int transposed;
+  int in_dtype;         /* dtype of x and w */
+  int out_dtype;        /* dtype of y (fwd) / dy (wgrad) */
+  int act;              /* CRD_ACT_NONE or CRD_ACT_SIGMOID applied after bias */
+  int accumulate;       /* y += result */
+  int out_nchw;         /* write y as NCHW (B,Cout,Ho,Wo); ldy ignored */
+} crd_conv_desc;
+
+/* generic CUDA-core path (any shape; the only path in fp32-exact mode) */
+CRD_API int crd_conv_fwd(const crd_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
+                 crd_stream_t stream);
+/* dw[n][(kh*KW+kw)*Cin + c] += sum_pixels dy[.,n] * x[.,c]  (fp32, atomically accumulated; caller zeroes) */
+CRD_API int crd_conv_wgrad(const crd_conv_desc* d, const void* x, const void* dy, float* dw, crd_stream_t stream);
+
+/* tcgen05 / TMEM / TMA path (bf16 in, fp32 accumulate): stride-1 KHxKW "same" convs and 1x1 GEMMs.
+ * Same contract as crd_conv_fwd (transposed=1 gives the stride-1 dgrad).  gn_sums (optional, fp32
+ * [B][Cout][2]) receives per-(sample, channel) sum / sum-of-squares of the fp32 accumulators. */
+CRD_API int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
+                    float* gn_sums, crd_stream_t stream);
+CRD_API int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const void* dy, float* dw, crd_stream_t stream);
+
+/* weight repacking between the reference's parameter layout and the kernels' K-major layout.
+ * mode 0 (fwd):   dst[co][tap][map[ci]] = w[co][ci][tap]            dst is [Cout][KH*KW][Cin_p]
+ * mode 1 (dgrad): dst[map[ci]][tap][co] = w[co][ci][tap]            dst is [Cin_p][KH*KW][Cout_p]
+ * map == NULL is the identity; dst must be zero-filled by the caller where unmapped. */
+CRD_API int crd_weight_pack(const float* w, void* dst, int dst_dtype, const int* map, int Cout, int Cin, int taps,
+                    int Cin_p, int Cout_p, int mode, crd_stream_t stream);
+/* grad[co][ci][tap] (+)= dwp[co][tap][map[ci]] */
+CRD_API int crd_weight_unpack_grad(const float* dwp, float* grad, const int* map, int Cout, int Cin, int taps,
+                           int Cin_p, int accumulate, crd_stream_t stream);
+/* db[n] += sum_m dy[m][n] */
+CRD_API int crd_col_sum(const void* dy, int dtype, float* db, long long M, int N, int ld, crd_stream_t stream);
+
+/* ---------------------------------------------------------------- GroupNorm (+GELU, +Dropout2d)
+ * nn.GroupNorm(C/16, C) everywhere: simplified_attention.py:23-24,70,117-118,162; utils.py:208-215.
+ * Protocol: per-(b,c) sums -> finalize to a per-(b,c) affine (a,b) -> apply in the consumer. */
+CRD_API int crd_chan_stats(const void* x, int dtype, float* sums /*[B][C][2], accumulated*/, int B, long long N,
+                   int C, int ld, crd_stream_t stream);
+CRD_API int crd_gn_finalize(const float* sums, const float* gamma, const float* beta, float* ab /*[B][C][2]*/,
+                    float* mean_rstd /*[B][G][2]*/, float* xbar /*[B][C] or NULL: token mean of the output*/,
+                    int B, int C, int G, long long N, float eps, crd_stream_t stream);
+/* y = act(a*x+b) * post[b][c] */
+CRD_API int crd_affine_act(const void* x, int in_dtype, void* y, int out_dtype, const float* ab, const float* post,
+                   int act, int B, long long N, int C, int ldx, int ldy, crd_stream_t stream);
+/* backward: dz = (dy + addbc[b][c]) * post * act'(a*x+b);  pq[b][c] += (sum dz, sum dz*x) */
+CRD_API int crd_gnact_bwd_reduce(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* ab,
+                         const float* post, const float* addbc, int act, float* pq, int B, long long N, int C,
+                         int lddy, int ldx, crd_stream_t stream);
+/* coef[b][c][3] = (A, Bq, Cq) with dx = A*dz + Bq*x + Cq ; dgamma/dbeta[c] += ... */
+CRD_API int crd_gn_bwd_finalize(const float* pq, const float* mean_rstd, const float* gamma, float* coef,
+                        float* dgamma, float* dbeta, int B, int C, int G, long long N, crd_stream_t stream);
+CRD_API int crd_gnact_bwd_apply(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* ab,
+                        const float* post, const float* addbc, int act, const float* coef, void* dx,
+                        int dx_dtype, int accumulate, int B, long long N, int C, int lddy, int ldx, int lddx,
+                        crd_stream_t stream);
+
+/* ---------------------------------------------------------------- encoder block pieces
+ * DWConv (simplified_attention.py:313-323) fused with the preceding GroupNorm apply (Mlp.norm1, :36). */
+CRD_API int crd_dwconv3x3_fwd(const void* x, int dtype, const float* ab, const float* w /*[C][9]*/, const float* bias,
+                      void* y, int B, int H, int W, int C, crd_stream_t stream);
+CRD_API int crd_dwconv3x3_bwd_input(const void* dy, int dtype, const float* w, void* dxn, int B, int H, int W, int C,
+                            crd_stream_t stream);
+CRD_API int crd_dwconv3x3_bwd_weight(const void* dy, int dtype, const void* x, const float* ab, float* dw, float* db,
+                             int B, int H, int W, int C, crd_stream_t stream);
+/* Attention_MaxPool (simplified_attention.py:90-109), algebraically reduced:
+ * s[b,n] = scale * sum_h max_m q_h[b,n,:].k_h[b,m,:] ; idx = argmax key per head */
+CRD_API int crd_attn_qkmax_fwd(const void* q, const void* k, int dtype, float* s, unsigned short* idx, int B, int N,
+                       int M, int C, int heads, float scale, crd_stream_t stream);
+CRD_API int crd_attn_qkmax_bwd(const float* ds, const void* q, const void* k, int dtype, const unsigned short* idx,
+                       void* dq, float* dk /*[B][M][C] accumulated*/, int B, int N, int M, int C, int heads,
+                       float scale, crd_stream_t stream);
+/* pv[b][o] = sum_c Wp[o][c] * xbar[b][c]   (proj applied to the token-mean "v", :103,108) */
+CRD_API int crd_attn_pv_fwd(const float* xbar, const float* Wp, float* pv, int B, int C, crd_stream_t stream);
+/* dWp[o][c] += sum_b dpv[b][o]*xbar[b][c] ; dxbar[b][c] = dxbar_scale * sum_o Wp[o][c]*dpv[b][o] */
+CRD_API int crd_attn_pv_bwd(const float* dpv, const float* xbar, const float* Wp, float* dWp, float* dxbar,
+                    float dxbar_scale, int B, int C, crd_stream_t stream);
+/* xout = x + dp[b] * (pv[b][c]*s[b][n] + bp[c])   (Block.forward :143) */
+CRD_API int crd_attn_out_residual(const float* x, const float* pv, const float* s, const float* bp, const float* dp,
+                          float* xout, int B, int N, int C, crd_stream_t stream);
+/* given dx (grad of xout): ds[b][n] = dp*sum_c dx*pv ; dpv[b][c] += dp*sum_n dx*s ; dbp[c] += dp*sum dx */
+CRD_API int crd_attn_out_bwd(const float* dx, const float* pv, const float* s, const float* dp, float* ds, float* dpv,
+                     float* dbp, float* tmp /*[B][C][2] scratch*/, int B, int N, int C, crd_stream_t stream);
+/* xout = x + dp[b]*y   (Block.forward :144) ; and its backward dy = dp[b]*dx */
+CRD_API int crd_residual_add(const float* x, const void* y, int y_dtype, const float* dp, float* xout, int B,
+                     long long N, int C, crd_stream_t stream);
+CRD_API int crd_scale_cast(const float* dx, const float* dp, void* dy, int dy_dtype, int B, long long N, int C,
+                   crd_stream_t stream);
+/* generic elementwise accumulate: dst(f32) += src */
+CRD_API int crd_add_f32(float* dst, const void* src, int src_dtype, long long n, crd_stream_t stream);
+
+/* ---------------------------------------------------------------- decoder pieces
+ * nn.Upsample(scale_factor=2, mode='bicubic') (utils.py:241,251), align_corners=False, A=-0.75. */
+CRD_API int crd_bicubic2x_fwd(const void* x, void* y, int dtype, int B, int H, int W, int C, int ldx, int ldy,
+                      crd_stream_t stream);
+CRD_API int crd_bicubic2x_bwd(const void* dy, void* dx, int dtype, int accumulate, int B, int H, int W, int C, int lddy,
+                      int lddx, crd_stream_t stream);
+/* Depth_Activation.conv_2 (utils.py:283,288): 3x3, Cin -> 1, bias; y fp32 (B,1,H,W) */
+CRD_API int crd_conv3x3_c1_fwd(const void* x, int dtype, const float* w /*[9][Cin]*/, const float* bias, float* y,
+                       int B, int H, int W, int Cin, int ldx, crd_stream_t stream);
+CRD_API int crd_conv3x3_c1_bwd(const float* dy, const void* x, int dtype, const float* w, void* dx, float* dw,
+                       float* db, int B, int H, int W, int Cin, int ldx, int lddx, crd_stream_t stream);
+/* dx = dy * y * (1-y) (y = sigmoid output) */
+CRD_API int crd_sigmoid_bwd(const void* dy, const void* y, void* dx, int dtype, long long n, crd_stream_t stream);
+/* Seg_Block (utils.py:95-100): map = argmax_c(logits)/ncls ; written to a channel of an NHWC buffer and/or
+ * an fp32 (B,1,H,W) tensor */
+CRD_API int crd_argmax_map(const void* logits, int dtype, int ld, int ncls, void* dst, int dst_dtype, int ld_dst,
+                   float* dst_f32, long long npix, crd_stream_t stream);
+
+/* ---------------------------------------------------------------- losses
+ * MaskedSmoothL1Loss (loss_funcs.py:77-91), MaskedMSELoss (:36-46), MaskedFocalLoss (:14-34). */
+CRD_API int crd_masked_l1_fwd(const float* pred, const float* target, float* acc /*[3]: sum smoothl1, count, sum sq*/,
+                      long long n, crd_stream_t stream);
+CRD_API int crd_masked_l1_bwd(const float* pred, const float* target, const float* acc, const float* gout, float* dpred,
+                      long long n, crd_stream_t stream);
+CRD_API int crd_ce_fwd(const float* logits /*NCHW*/, const long long* target, float* acc /*[2]: sum nll, count*/,
+               int B, int C, long long HW, int ignore_index, crd_stream_t stream);
+CRD_API int crd_ce_bwd(const float* logits, const long long* target, const float* acc, const float* gout, float gamma,
+               float* dlogits, int B, int C, long long HW, int ignore_index, crd_stream_t stream);
+/* out[0] = acc[0]/acc[1] ; (focal) out[0] = (1-exp(-ce))^gamma * ce ; (rmse) out[1] = sqrt(acc[2]/acc[1]) */
+CRD_API int crd_loss_finalize(const float* acc, float* out, int kind, float gamma, crd_stream_t stream);
+
+/* ---------------------------------------------------------------- diffGradNorm (diffGradNorm.py:41-113)
+ * multi-tensor: table rows describe (param, grad, exp_avg, exp_avg_sq, previous_grad, numel). */
+typedef struct {
+  float* p; const float* g; float* m; float* v; float* prev;
+  long long numel;
+} crd_opt_tensor;
+typedef struct { int tensor; int pad; long long start; } crd_opt_chunk;   /* chunk of CRD_OPT_CHUNK elements */
+#define CRD_OPT_CHUNK 16384
+CRD_API int crd_mt_sumsq(const crd_opt_tensor* table, const crd_opt_chunk* chunks, int nchunks, float* sumsq,
+                 crd_stream_t stream);
+/* step_size = lr*sqrt(1-beta2^t)/((1-beta1^t)+1e-8) (diffGradNorm.py:108); egn_in/egn_out: per-tensor
+ * exp_grad_norm before/after (ping-pong so every chunk of a tensor sees the same input) */
+CRD_API int crd_diffgradnorm_update(const crd_opt_tensor* table, const crd_opt_chunk* chunks, int nchunks,
+                            const float* sumsq, const float* egn_in, float* egn_out, float step_size,
+                            float beta1, float beta2, float eps, crd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
