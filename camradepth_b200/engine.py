@@ -80,6 +80,17 @@ class Engine:
         self._build_layers()
         self.fwd_arena = None
         self.bwd_arena = None
+        # optional CUDA-event timing of selected conv launches: {(kind, weight name): [(ev0, ev1), ...]}
+        self.timed = None
+
+    def _timed(self, kind, name):
+        if self.timed is None or (kind, name) not in self.timed:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        self.timed[(kind, name)].append((e0, e1))
+        e0.record()
+        return e1
 
     # ------------------------------------------------------------------ layer table
     def _build_layers(self):
@@ -189,14 +200,20 @@ class Engine:
         d = ops.make_desc(x, y, L["cin_p"], L["cout"], L["k"], L["k"], L["stride"], L["pad"], 0, act, accumulate,
                           out_nchw)
         b = None if bias is None else self.P[bias].detach()
+        ev = self._timed("fwd", name)
         ops.conv_fwd(d, x, w, b, y, use_tc=self.use_tc and self._tc_ok(L, x, y))
+        if ev is not None:
+            ev.record()
 
     def conv_dgrad(self, dy, name, dx, accumulate):
         L = self.L[name]
         w = self.wpack(name, 1)
         d = ops.make_desc(dy, dx, L["cout_p"], L["cin_p"], L["k"], L["k"], L["stride"], L["pad"], 1, 0,
                           int(accumulate), 0)
+        ev = self._timed("dgrad", name)
         ops.conv_fwd(d, dy, w, None, dx, use_tc=self.use_tc and self._tc_ok(L, dy, dx))
+        if ev is not None:
+            ev.record()
 
     def conv_wgrad(self, x, dy, name, bias=None):
         L = self.L[name]
@@ -204,7 +221,10 @@ class Engine:
         g = self.pg[name]
         dwp = g.view(L["cout"], L["cin"]) if direct else self.bwd_arena.take(L["cout"], L["taps"] * L["cin_p"])
         d = ops.make_desc(x, dy, L["cin_p"], L["cout"], L["k"], L["k"], L["stride"], L["pad"], 0, 0, 0, 0)
+        ev = self._timed("wgrad", name)
         ops.conv_wgrad(d, x, dy, dwp, use_tc=self.use_tc and self._tc_ok(L, x, dy))
+        if ev is not None:
+            ev.record()
         if not direct:
             ops.weight_unpack_grad(dwp, g, self._cmap(name), L["cout"], L["cin"], L["taps"], L["cin_p"], False)
         if bias is not None:
