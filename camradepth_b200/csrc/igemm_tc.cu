@@ -1,12 +1,367 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution (bf16 operands, fp32 accumulation in tensor memory).
-// (under construction: entry points report "unsupported" until the kernels land)
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in
+// tensor memory).  Covers the stride-1 KHxKW "same" convolutions of the decoder (forward and, with
+// transposed=1, data gradient) and every 1x1 contraction of the encoder.
+//
+// GEMM view: D[128 pixels][BN <= 128 channels] += A[128][64] * B[BN][64]^T per (tap, 64-channel chunk).
+//   A: activations, NHWC bf16.  One TMA box {64 ch, TW px, TH rows, 1 image} per (tap, chunk); the tap
+//      shift is applied to the box coordinates and out-of-bounds pixels / channels are zero-filled by
+//      the TMA unit, so the halo and the channel tail need no code.  Lands in smem as 128 rows x 128 B,
+//      SWIZZLE_128B = the canonical K-major UMMA operand layout.
+//   B: packed weights [Cout][taps*Cin] (K-major), box {64, BN}.
+//   D: 128 lanes x BN columns of TMEM, drained by four epilogue warps (tcgen05.ld 32x32b), bias /
+//      sigmoid / accumulate applied in registers, 16-byte stores into the (possibly sliced) NHWC output.
+// Roles: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2-5 = epilogue.  STAGES-deep smem ring with full/empty mbarriers; tcgen05.commit releases slots.
+#include <cuda.h>
 #include "common.cuh"
 #include "../../include/camradepth_b200.h"
 
+namespace {
+
+constexpr int TC_BM = 128;          // pixels per tile
+constexpr int TC_BK = 64;           // channels per k-chunk (128 bytes of bf16 = one swizzle row)
+constexpr int TC_STAGES = 3;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
+constexpr int TC_B_BYTES = 128 * TC_BK * 2;
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 192;
+
+struct TcParams {
+  int flat;                 // 1: A is a 2-D [pixels][C] tensor (1x1 conv); 0: 4-D patch mode
+  int TW, TH;               // spatial patch (TW*TH == 128)
+  int tiles_w, tiles_h;
+  int Ho, Wo;
+  long long P;              // total pixels (flat mode)
+  int KH, KW, pad, transposed;
+  int kchunks;              // ceil(Cin / 64)
+  int Cin;                  // K stride between taps in the packed weights
+  int Cout;
+  int bn;                   // UMMA N of this launch (multiple of 16, <= 128)
+  int ldy, out_f32, act, accumulate;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14),
+// LBO>>4 [16,30) (unused for swizzled K-major), SBO>>4 [32,46) = 1024 B between 8-row groups,
+// version=1 [46,48), layout_type=2 (SWIZZLE_128B) [61,64).
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format=F32 [4,6), a/b_format=BF16 [7,10)/[10,13),
+// a/b major = K (0), N>>3 [17,23), M>>4 [24,29).
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const TcParams p, const float* __restrict__ bias, void* __restrict__ yv) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024-B alignment
+  const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;
+  // barrier layout: full[STAGES], empty[STAGES], tmem_full, then the TMEM base address word
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * TC_STAGES, bar_tmem = bars + 16 * TC_STAGES;
+  const uint32_t tmem_slot = bar_tmem + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * 128;
+  // tile coordinates
+  int b = 0, oh0 = 0, ow0 = 0;
+  long long m0 = 0;
+  if (p.flat) {
+    m0 = (long long)blockIdx.x * TC_BM;
+  } else {
+    int t = blockIdx.x;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h; t /= p.tiles_h;
+    b = t; oh0 = th * p.TH; ow0 = tw * p.TW;
+  }
+  const int taps = p.KH * p.KW;
+  const int nk = taps * p.kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_tmem, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) {   // TMEM: 128 fp32 columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      const uint32_t tx = TC_A_BYTES + (uint32_t)p.bn * TC_BK * 2;
+      for (int it = 0; it < nk; it++) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        const int tap = it / p.kchunks, c0 = (it - tap * p.kchunks) * TC_BK;
+        const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+        mbar_expect_tx(bar_full + 8 * s, tx);
+        if (p.flat) {
+          tma_load_2d(sa, &map_a, bar_full + 8 * s, c0, (int)m0);
+        } else {
+          const int kh = tap / p.KW, kw = tap - kh * p.KW;
+          const int dh = p.transposed ? (p.pad - kh) : (kh - p.pad);
+          const int dw = p.transposed ? (p.pad - kw) : (kw - p.pad);
+          tma_load_4d(sa, &map_a, bar_full + 8 * s, c0, ow0 + dw, oh0 + dh, b);
+        }
+        tma_load_2d(sb, &map_b, bar_full + 8 * s, tap * p.Cin + c0, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc_bf16(128, p.bn);
+      for (int it = 0; it < nk; it++) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+        const uint64_t ad = umma_desc_kmajor_sw128(sa), bd = umma_desc_kmajor_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; k++) {
+          // advance 16 bf16 (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 address field
+          umma_bf16_ss(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) != 0);
+        }
+        umma_commit(bar_empty + 8 * s);           // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(bar_tmem);                      // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane group = warp % 4 =====
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    mbar_wait(bar_tmem, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    long long pix;
+    bool ok;
+    if (p.flat) {
+      pix = m0 + row;
+      ok = pix < p.P;
+    } else {
+      const int ty = row / p.TW, tx = row - ty * p.TW;
+      const int oh = oh0 + ty, ow = ow0 + tx;
+      ok = oh < p.Ho && ow < p.Wo;
+      pix = ((long long)b * p.Ho + oh) * p.Wo + ow;
+    }
+    for (int c = 0; c < p.bn; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (!ok) continue;
+      const int n = n0 + c;
+      if (n >= p.Cout) continue;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        v[j] = __uint_as_float(r[j]);
+        if (bias && n + j < p.Cout) v[j] += bias[n + j];
+        if (p.act == CRD_ACT_SIGMOID) v[j] = sigmoid_f(v[j]);
+      }
+      const int nvalid = min(16, (p.Cout - n + 7) / 8 * 8);     // output buffers are padded to 8 channels
+      if (p.out_f32) {
+        float* yp = reinterpret_cast<float*>(yv) + pix * p.ldy + n;
+        for (int j = 0; j < nvalid; j += 8) {
+          float o[8];
+          if (p.accumulate) { load8(yp + j, o); } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) o[q] = 0.f;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; q++) o[q] += (n + j + q < p.Cout) ? v[j + q] : 0.f;
+          store8(yp + j, o);
+        }
+      } else {
+        bf16* yp = reinterpret_cast<bf16*>(yv) + pix * p.ldy + n;
+        for (int j = 0; j < nvalid; j += 8) {
+          float o[8];
+          if (p.accumulate) { load8(yp + j, o); } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) o[q] = 0.f;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; q++) o[q] += (n + j + q < p.Cout) ? v[j + q] : 0.f;
+          store8(yp + j, o);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+  }
+}
+
+// ------------------------------------------------------------------ host side: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+             const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -10;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -11 - (int)r;
+}
+
+}  // namespace
+
 extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                                float* gn_sums, crd_stream_t stream) {
-  return -3;
+  CRD_REQUIRE(d && x && w && y);
+  CRD_REQUIRE(gn_sums == nullptr);                       // fused GroupNorm statistics: not in this revision
+  CRD_REQUIRE(d->in_dtype == CRD_BF16 && (d->out_dtype == CRD_BF16 || d->out_dtype == CRD_F32));
+  CRD_REQUIRE(d->stride == 1 && !d->out_nchw && d->Ho == d->H && d->Wo == d->W);
+  CRD_REQUIRE(d->Cin % 8 == 0 && d->ldx % 8 == 0 && d->ldy % 8 == 0);
+  CRD_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)y & 15) == 0);
+  CRD_REQUIRE(d->KH == d->KW && 2 * d->pad == d->KH - 1);
+  const long long P = (long long)d->B * d->H * d->W;
+  if (P == 0) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  TcParams p;
+  p.flat = (d->KH == 1);
+  p.KH = d->KH; p.KW = d->KW; p.pad = d->pad; p.transposed = d->transposed;
+  p.Ho = d->Ho; p.Wo = d->Wo; p.P = P;
+  p.Cin = d->Cin; p.Cout = d->Cout;
+  p.kchunks = (d->Cin + TC_BK - 1) / TC_BK;
+  p.ldy = d->ldy; p.out_f32 = d->out_dtype == CRD_F32; p.act = d->act; p.accumulate = d->accumulate;
+  // spatial patch: 16 wide unless the image is narrower
+  p.TW = d->W >= 16 ? 16 : (d->W >= 8 ? 8 : 4);
+  p.TH = TC_BM / p.TW;
+  p.tiles_w = (d->W + p.TW - 1) / p.TW;
+  p.tiles_h = (d->H + p.TH - 1) / p.TH;
+  CUtensorMap map_a, map_b;
+  int rc;
+  if (p.flat) {
+    cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)P};
+    cuuint64_t str[1] = {(cuuint64_t)d->ldx * 2};
+    cuuint32_t box[2] = {TC_BK, TC_BM};
+    rc = make_map(&map_a, x, 2, dims, str, box);
+  } else {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t str[3] = {(cuuint64_t)d->ldx * 2, (cuuint64_t)d->W * d->ldx * 2, (cuuint64_t)d->H * d->W * d->ldx * 2};
+    cuuint32_t box[4] = {TC_BK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    rc = make_map(&map_a, x, 4, dims, str, box);
+  }
+  if (rc) return rc;
+  const int Ktot = d->KH * d->KW * d->Cin;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int gx = p.flat ? crd_div_up(P, TC_BM) : p.tiles_w * p.tiles_h * d->B;
+  // N is covered in tiles of 128; a ragged last tile runs as its own launch with a smaller UMMA N
+  const int nfull = d->Cout / 128, rem = d->Cout - nfull * 128;
+  for (int part = 0; part < 2; part++) {
+    const int ntiles = part == 0 ? nfull : (rem ? 1 : 0);
+    if (!ntiles) continue;
+    const int nbase = part == 0 ? 0 : nfull * 128;
+    p.bn = part == 0 ? 128 : (rem + 15) / 16 * 16;
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)(d->Cout - nbase)};
+    cuuint64_t str[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t box[2] = {TC_BK, (cuuint32_t)p.bn};
+    rc = make_map(&map_b, (const bf16*)w + (long long)nbase * Ktot, 2, dims, str, box);
+    if (rc) return rc;
+    TcParams q = p;
+    q.Cout = d->Cout - nbase;
+    const float* bp = bias ? bias + nbase : nullptr;
+    void* yp = d->out_dtype == CRD_F32 ? (void*)((float*)y + nbase) : (void*)((bf16*)y + nbase);
+    conv_tc_kernel<<<dim3(gx, ntiles), TC_THREADS, TC_SMEM, s>>>(map_a, map_b, q, bp, yp);
+    CRD_LAUNCH_CHECK();
+  }
+  return 0;
 }
+
 extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const void* dy, float* dw,
                                  crd_stream_t stream) {
   return -3;

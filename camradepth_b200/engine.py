@@ -16,6 +16,7 @@ Data layout in HBM (bf16 mode; fp32 mode stores everything as fp32):
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -76,12 +77,14 @@ class Engine:
         self.device = None
         self._packs = {}
         self._maps = {}
-        self.use_tc = False
+        self.use_tc = precision == "bf16" and os.environ.get("CAMRADEPTH_TC", "1") == "1"
+        self.use_tc_wgrad = False
         self._build_layers()
         self.fwd_arena = None
         self.bwd_arena = None
         # optional CUDA-event timing of selected conv launches: {(kind, weight name): [(ev0, ev1), ...]}
         self.timed = None
+        self._grad_epoch = 0
 
     def _timed(self, kind, name):
         if self.timed is None or (kind, name) not in self.timed:
@@ -176,7 +179,7 @@ class Engine:
         if mode == 0 and dtype == torch.float32 and L["taps"] == 1 and L["cmap"] is None and L["cin_p"] == L["cin"]:
             return p.detach()
         key = (name, mode, dtype)
-        ver = (p._version, p.data_ptr(), WEIGHT_EPOCH[0])
+        ver = (p._version, p.data_ptr(), WEIGHT_EPOCH[0], self._grad_epoch)
         ent = self._packs.get(key)
         if ent is not None and ent[1] == ver:
             return ent[0]
@@ -192,7 +195,9 @@ class Engine:
         return dst
 
     def _tc_ok(self, L, x, y_or_dy):
-        return False
+        """tcgen05 path: bf16 operands, stride-1 'same' KxK or 1x1 contractions."""
+        return (self.tdtype == torch.bfloat16 and L["stride"] == 1 and L["k"] in (1, 3) and
+                2 * L["pad"] == L["k"] - 1 and x.dtype == torch.bfloat16)
 
     def conv(self, x, name, y, bias=None, act=0, accumulate=0, out_nchw=0):
         L = self.L[name]
@@ -222,7 +227,7 @@ class Engine:
         dwp = g.view(L["cout"], L["cin"]) if direct else self.bwd_arena.take(L["cout"], L["taps"] * L["cin_p"])
         d = ops.make_desc(x, dy, L["cin_p"], L["cout"], L["k"], L["k"], L["stride"], L["pad"], 0, 0, 0, 0)
         ev = self._timed("wgrad", name)
-        ops.conv_wgrad(d, x, dy, dwp, use_tc=self.use_tc and self._tc_ok(L, x, dy))
+        ops.conv_wgrad(d, x, dy, dwp, use_tc=self.use_tc_wgrad and self._tc_ok(L, x, dy))
         if ev is not None:
             ev.record()
         if not direct:
@@ -525,6 +530,10 @@ class Engine:
         if H % 32 or W % 32:
             raise RuntimeError(f"Sizes of tensors must match: H and W must be multiples of 32, got {H}x{W}")
         x = x.detach().contiguous().float()
+        if save:
+            # training forward: parameters may have been updated through `.data` (no version bump, e.g. the
+            # reference's own optimizer), so packed copies are rebuilt every grad-enabled forward
+            self._grad_epoch += 1
         self.fwd_arena.reset()
         if train:
             dps, d2s = masks if masks is not None else self.make_masks(B)

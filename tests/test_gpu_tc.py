@@ -1,0 +1,102 @@
+"""tcgen05/TMA implicit-GEMM kernels (GPU): parity against F.conv2d on bf16-rounded operands and against
+the CUDA-core path, over the decoder / encoder shapes incl. ragged channel counts, sliced buffers,
+partial spatial tiles, accumulate and the sigmoid / fp32-output epilogues."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.test_gpu_ops import dev, rel, nhwc, nchw, rnd, r8
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+TC_CASES = [
+    # B, Cin, H, W, Cout, k
+    (2, 136, 16, 32, 96, 3),
+    (1, 232, 24, 48, 64, 3),
+    (2, 296, 8, 16, 128, 3),
+    (2, 129, 12, 20, 96, 3),      # Cin padded 129 -> 136, partial spatial tiles
+    (1, 416, 6, 13, 96, 3),       # tiny image: one partial tile
+    (2, 128, 10, 14, 21, 3),      # ragged N (21 -> UMMA N 32)
+    (2, 128, 16, 16, 32, 3),
+    (3, 160, 6, 13, 160, 1),      # 1x1, N = 128 + 32
+    (2, 64, 48, 104, 512, 1),     # fc1-like
+    (2, 1024, 6, 13, 256, 1),     # fc2-like, long K
+    (1, 256, 3, 5, 256, 1),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc_fwd_and_dgrad(case):
+    from camradepth_b200 import ops
+    B, Cin, H, W, Cout, k = case
+    pad = k // 2
+    torch.manual_seed(0)
+    d = dev()
+    x = torch.randn(B, Cin, H, W, device=d)
+    w = torch.randn(Cout, Cin, k, k, device=d) / math.sqrt(Cin * k * k)
+    bias = torch.randn(Cout, device=d)
+    xr, wr = rnd(x, BF).requires_grad_(True), rnd(w, BF).requires_grad_(True)
+    yr = F.conv2d(xr, wr, bias, padding=pad)
+    cin_p, cout_p = r8(Cin), r8(Cout)
+    xb = nhwc(x, BF, cin_p + 8)[..., :cin_p]
+    wp = torch.zeros(Cout, k * k * cin_p, dtype=BF, device=d)
+    ops.weight_pack(w, wp, None, Cout, Cin, k * k, cin_p, cout_p, 0)
+    ybuf = torch.zeros(B, H, W, cout_p + 16, dtype=BF, device=d)
+    y = ybuf[..., 8:8 + cout_p]
+    desc = ops.make_desc(xb, y, cin_p, Cout, k, k, 1, pad)
+    ops.conv_fwd(desc, xb, wp, bias, y, use_tc=True)
+    torch.cuda.synchronize()
+    assert rel(nchw(y, Cout), yr) < 5e-3, rel(nchw(y, Cout), yr)
+    assert float(ybuf[..., :8].abs().max()) == 0 and float(ybuf[..., 8 + cout_p:].abs().max()) == 0
+    # same thing on the CUDA-core path: the two must agree to accumulation-order noise
+    y2 = torch.zeros(B, H, W, cout_p, dtype=BF, device=d)
+    desc2 = ops.make_desc(xb, y2, cin_p, Cout, k, k, 1, pad)
+    ops.conv_fwd(desc2, xb, wp, bias, y2)
+    assert rel(y[..., :Cout], y2[..., :Cout]) < 4e-3
+    # fp32 output + sigmoid epilogue
+    y3 = torch.zeros(B, H, W, cout_p, dtype=torch.float32, device=d)
+    desc3 = ops.make_desc(xb, y3, cin_p, Cout, k, k, 1, pad, act=ops.ACT_SIGMOID)
+    ops.conv_fwd(desc3, xb, wp, bias, y3, use_tc=True)
+    assert rel(nchw(y3, Cout), torch.sigmoid(yr)) < 1e-4
+    # dgrad = transposed mode, accumulated on top of ones
+    gy = torch.randn_like(yr)
+    (gx_ref,) = torch.autograd.grad(yr, xr, rnd(gy, BF))
+    dy = nhwc(gy, BF, cout_p)
+    wd = torch.zeros(cin_p, k * k * cout_p, dtype=BF, device=d)
+    ops.weight_pack(w, wd, None, Cout, Cin, k * k, cin_p, cout_p, 1)
+    dx = torch.ones(B, H, W, cin_p, dtype=BF, device=d)
+    desc4 = ops.make_desc(dy, dx, cout_p, cin_p, k, k, 1, pad, transposed=1, accumulate=1)
+    ops.conv_fwd(desc4, dy, wd, None, dx, use_tc=True)
+    assert rel(nchw(dx, Cin) - 1.0, gx_ref) < 2e-2
+
+
+def test_conv_tc_large_matches_simt():
+    """BASELINE-sized layer: depth_upsample[4] layer 2 (Cin 296 -> 128 at 192x416), B=2."""
+    from camradepth_b200 import ops
+    d = dev()
+    torch.manual_seed(1)
+    B, Cin, H, W, Cout = 2, 296, 192, 416, 128
+    xb = (torch.randn(B, H, W, Cin, device=d) * 0.5).to(BF)
+    wp = (torch.randn(Cout, 9 * Cin, device=d) / math.sqrt(9 * Cin)).to(BF)
+    y1 = torch.empty(B, H, W, Cout, dtype=BF, device=d)
+    y2 = torch.empty(B, H, W, Cout, dtype=BF, device=d)
+    ops.conv_fwd(ops.make_desc(xb, y1, Cin, Cout, 3, 3, 1, 1), xb, wp, None, y1, use_tc=True)
+    ops.conv_fwd(ops.make_desc(xb, y2, Cin, Cout, 3, 3, 1, 1), xb, wp, None, y2)
+    torch.cuda.synchronize()
+    assert rel(y1, y2) < 4e-3
+    # linearity (size-independent property): conv(2x) == 2 conv(x) exactly in bf16 (power-of-two scale)
+    y3 = torch.empty_like(y1)
+    x2 = (xb.float() * 2).to(BF)
+    ops.conv_fwd(ops.make_desc(x2, y3, Cin, Cout, 3, 3, 1, 1), x2, wp, None, y3, use_tc=True)
+    assert torch.equal(y3.float(), y1.float() * 2)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(5):
+        ops.conv_fwd(ops.make_desc(xb, y1, Cin, Cout, 3, 3, 1, 1), xb, wp, None, y1, use_tc=True)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / 5
+    print(f"tc conv 296->128 @192x416 B=2: {ms:.3f} ms, {2*B*H*W*Cout*9*Cin/ms/1e9:.1f} TFLOP/s")
