@@ -362,7 +362,225 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
   return 0;
 }
 
+namespace {
+
+// ====================================================================================================
+// Weight gradient: dW[co][(kh,kw,ci)] = sum_pixels dY[pix][co] * X[pix + shift(kh,kw)][ci]
+// GEMM view per CTA: D[128 co][nblk*64] += A[128][128 px] * B[nblk*64][128 px]^T, reduction over pixels.
+// Both operands are MN-major: a TMA box {64 ch, TW, TH, 1} lands as [128 px][64 ch] = 128 rows x 128 B,
+// which IS the canonical MN-major SWIZZLE_128B UMMA layout (8-row groups 1024 B apart along K = SBO;
+// 64-channel column blocks one box apart along M/N = LBO).  One CTA owns (kh, one 64-channel chunk) and
+// the KW shifted copies of X as its N blocks (or up to three 64-channel chunks of a 1x1 contraction), so
+// dY is fetched once per KW taps.  The pixel range is split over blockIdx.x; partial sums meet in fp32
+// with red.global.add (split-K), the accumulator lives in TMEM for the whole pixel loop.
+constexpr int WG_STAGES = 2;
+constexpr int WG_BLK_BYTES = 128 * 64 * 2;                      // one [128 px][64 ch] box
+constexpr int WG_STAGE_BYTES = 5 * WG_BLK_BYTES;                // 2 dY blocks + 3 X blocks
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+
+struct WgParams {
+  int flat, TW, TH, tiles_w, tiles_h;
+  long long total_tiles, tiles_per_split;
+  int KH, KW, pad;
+  int Cin, Cout, kchunks;
+  int mblocks;              // 64-channel blocks of dY in this launch (1 or 2)
+  long long Ktot;           // row stride of dw
+};
+
+// MN-major, SWIZZLE_128B descriptor: LBO = bytes between 64-element column blocks, SBO = 1024 B between
+// 8-row groups along K.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                const WgParams p, float* __restrict__ dw) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + WG_STAGES * WG_STAGE_BYTES;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * WG_STAGES, bar_tmem = bars + 16 * WG_STAGES;
+  const uint32_t tmem_slot = bar_tmem + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // work column: (chunk, kh) for KxK; a group of up to 3 chunks for 1x1
+  int c0, kh = 0, nblk;
+  if (p.KH > 1) {
+    const int chunk = blockIdx.y / p.KH;
+    kh = blockIdx.y - chunk * p.KH;
+    c0 = chunk * 64;
+    nblk = p.KW;
+  } else {
+    c0 = blockIdx.y * 192;
+    nblk = min(3, p.kchunks - blockIdx.y * 3);
+  }
+  const int co0 = blockIdx.z * 128;
+  const int mblocks = min(p.mblocks, (p.Cout - co0 + 63) / 64);
+  const long long t_begin = (long long)blockIdx.x * p.tiles_per_split;
+  const long long t_end = min(p.total_tiles, t_begin + p.tiles_per_split);
+  const int ntiles = (int)max(0LL, t_end - t_begin);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_tmem, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (ntiles > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const uint32_t tx = (uint32_t)(mblocks + nblk) * WG_BLK_BYTES;
+        for (int it = 0; it < ntiles; it++) {
+          const int s = it % WG_STAGES;
+          const uint32_t ph = (it / WG_STAGES) & 1;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t sa = base + s * WG_STAGE_BYTES, sb = sa + 2 * WG_BLK_BYTES;
+          const uint32_t bar = bar_full + 8 * s;
+          mbar_expect_tx(bar, tx);
+          long long t = t_begin + it;
+          if (p.flat) {
+            const int m0 = (int)(t * 128);
+            for (int j = 0; j < mblocks; j++) tma_load_2d(sa + j * WG_BLK_BYTES, &map_dy, bar, co0 + 64 * j, m0);
+            for (int j = 0; j < nblk; j++) tma_load_2d(sb + j * WG_BLK_BYTES, &map_x, bar, c0 + 64 * j, m0);
+          } else {
+            const int tw = (int)(t % p.tiles_w); t /= p.tiles_w;
+            const int th = (int)(t % p.tiles_h); t /= p.tiles_h;
+            const int b = (int)t, oh0 = th * p.TH, ow0 = tw * p.TW;
+            for (int j = 0; j < mblocks; j++)
+              tma_load_4d(sa + j * WG_BLK_BYTES, &map_dy, bar, co0 + 64 * j, ow0, oh0, b);
+            for (int j = 0; j < nblk; j++)
+              tma_load_4d(sb + j * WG_BLK_BYTES, &map_x, bar, c0, ow0 + j - p.pad, oh0 + kh - p.pad, b);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // M = 128 (rows beyond the loaded dY blocks hold stale smem and are ignored by the epilogue)
+        const uint32_t idesc = umma_idesc_bf16(128, nblk * 64) | (1u << 15) | (1u << 16);   // A, B MN-major
+        for (int it = 0; it < ntiles; it++) {
+          const int s = it % WG_STAGES;
+          const uint32_t ph = (it / WG_STAGES) & 1;
+          mbar_wait(bar_full + 8 * s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = base + s * WG_STAGE_BYTES, sb = sa + 2 * WG_BLK_BYTES;
+#pragma unroll
+          for (int k = 0; k < 8; k++) {       // 16 pixels (two 8-row groups = 2048 B) per MMA
+            const uint64_t ad = umma_desc_mnmajor_sw128(sa + k * 2048, WG_BLK_BYTES);
+            const uint64_t bd = umma_desc_mnmajor_sw128(sb + k * 2048, WG_BLK_BYTES);
+            umma_bf16_ss(tmem_base, ad, bd, idesc, (it | k) != 0);
+          }
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_tmem);
+      }
+    } else {
+      const int lg = warp & 3;
+      const int co = co0 + lg * 32 + lane;
+      mbar_wait(bar_tmem, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c = 0; c < nblk * 64; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (co >= p.Cout || lg * 32 + lane >= mblocks * 64) continue;
+        const int j = c >> 6, col = c & 63;
+        long long kbase;
+        int cc;
+        if (p.KH > 1) { cc = c0 + col; kbase = (long long)(kh * p.KW + j) * p.Cin + cc; }
+        else { cc = c0 + 64 * j + col; kbase = cc; }
+        float* dst = dw + (long long)co * p.Ktot + kbase;
+#pragma unroll
+        for (int q = 0; q < 16; q++)
+          if (cc + q < p.Cin) atomicAdd(dst + q, __uint_as_float(r[q]));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+  }
+}
+
+}  // namespace
+
 extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const void* dy, float* dw,
                                  crd_stream_t stream) {
-  return -3;
+  CRD_REQUIRE(d && x && dy && dw);
+  CRD_REQUIRE(d->in_dtype == CRD_BF16 && d->out_dtype == CRD_BF16);
+  CRD_REQUIRE(d->stride == 1 && !d->transposed && d->Ho == d->H && d->Wo == d->W);
+  CRD_REQUIRE(d->Cin % 8 == 0 && d->ldx % 8 == 0 && d->ldy % 8 == 0);
+  CRD_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0);
+  CRD_REQUIRE(d->KH == d->KW && 2 * d->pad == d->KH - 1 && d->KW <= 3);
+  const long long P = (long long)d->B * d->H * d->W;
+  if (P == 0) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  WgParams p;
+  p.flat = (d->KH == 1);
+  p.KH = d->KH; p.KW = d->KW; p.pad = d->pad;
+  p.Cin = d->Cin; p.Cout = d->Cout;
+  p.kchunks = (d->Cin + 63) / 64;
+  p.mblocks = d->Cout > 64 ? 2 : 1;
+  p.Ktot = (long long)d->KH * d->KW * d->Cin;
+  p.TW = d->W >= 16 ? 16 : (d->W >= 8 ? 8 : 4);
+  p.TH = 128 / p.TW;
+  p.tiles_w = (d->W + p.TW - 1) / p.TW;
+  p.tiles_h = (d->H + p.TH - 1) / p.TH;
+  p.total_tiles = p.flat ? (P + 127) / 128 : (long long)p.tiles_w * p.tiles_h * d->B;
+  CUtensorMap map_dy, map_x;
+  int rc;
+  if (p.flat) {
+    cuuint64_t dims[2] = {(cuuint64_t)d->Cout, (cuuint64_t)P};
+    cuuint64_t str[1] = {(cuuint64_t)d->ldy * 2};
+    cuuint32_t box[2] = {64, 128};
+    rc = make_map(&map_dy, dy, 2, dims, str, box);
+    if (rc) return rc;
+    cuuint64_t dims2[2] = {(cuuint64_t)d->Cin, (cuuint64_t)P};
+    cuuint64_t str2[1] = {(cuuint64_t)d->ldx * 2};
+    rc = make_map(&map_x, x, 2, dims2, str2, box);
+  } else {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t str[3] = {(cuuint64_t)d->ldy * 2, (cuuint64_t)d->W * d->ldy * 2, (cuuint64_t)d->H * d->W * d->ldy * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    rc = make_map(&map_dy, dy, 4, dims, str, box);
+    if (rc) return rc;
+    cuuint64_t dims2[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t str2[3] = {(cuuint64_t)d->ldx * 2, (cuuint64_t)d->W * d->ldx * 2, (cuuint64_t)d->H * d->W * d->ldx * 2};
+    rc = make_map(&map_x, x, 4, dims2, str2, box);
+  }
+  if (rc) return rc;
+  const int gy = p.flat ? (p.kchunks + 2) / 3 : p.kchunks * p.KH;
+  const int gz = (d->Cout + 127) / 128;
+  // split the pixel tiles so that ~2 waves of CTAs cover the 148 SMs; each split handles >= 4 tiles
+  long long want = (148LL * 2 + (long long)gy * gz - 1) / ((long long)gy * gz);
+  long long maxs = (p.total_tiles + 3) / 4;
+  long long splits = want < 1 ? 1 : (want > maxs ? maxs : want);
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (p.total_tiles + splits - 1) / splits;
+  splits = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  wgrad_tc_kernel<<<dim3((unsigned)splits, gy, gz), TC_THREADS, WG_SMEM, (cudaStream_t)stream>>>(map_dy, map_x, p, dw);
+  CRD_LAUNCH_CHECK();
+  return 0;
 }

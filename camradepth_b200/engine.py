@@ -78,7 +78,7 @@ class Engine:
         self._packs = {}
         self._maps = {}
         self.use_tc = precision == "bf16" and os.environ.get("CAMRADEPTH_TC", "1") == "1"
-        self.use_tc_wgrad = False
+        self.use_tc_wgrad = self.use_tc and os.environ.get("CAMRADEPTH_TC_WGRAD", "1") == "1"
         self._build_layers()
         self.fwd_arena = None
         self.bwd_arena = None

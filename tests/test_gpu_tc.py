@@ -63,7 +63,7 @@ def test_conv_tc_fwd_and_dgrad(case):
     assert rel(nchw(y3, Cout), torch.sigmoid(yr)) < 1e-4
     # dgrad = transposed mode, accumulated on top of ones
     gy = torch.randn_like(yr)
-    (gx_ref,) = torch.autograd.grad(yr, xr, rnd(gy, BF))
+    gx_ref, gw_ref = torch.autograd.grad(yr, (xr, wr), rnd(gy, BF))
     dy = nhwc(gy, BF, cout_p)
     wd = torch.zeros(cin_p, k * k * cout_p, dtype=BF, device=d)
     ops.weight_pack(w, wd, None, Cout, Cin, k * k, cin_p, cout_p, 1)
@@ -71,6 +71,19 @@ def test_conv_tc_fwd_and_dgrad(case):
     desc4 = ops.make_desc(dy, dx, cout_p, cin_p, k, k, 1, pad, transposed=1, accumulate=1)
     ops.conv_fwd(desc4, dy, wd, None, dx, use_tc=True)
     assert rel(nchw(dx, Cin) - 1.0, gx_ref) < 2e-2
+    # wgrad (both operands MN-major, split-K with fp32 atomics); dy read from a channel slice
+    dyb = torch.zeros(B, H, W, cout_p + 8, dtype=BF, device=d)
+    dyb[..., 8:] = dy
+    dys = dyb[..., 8:]
+    dwp = torch.zeros(Cout, k * k * cin_p, dtype=torch.float32, device=d)
+    ops.conv_wgrad(ops.make_desc(xb, dys, cin_p, Cout, k, k, 1, pad), xb, dys, dwp, use_tc=True)
+    gw = torch.empty_like(w)
+    ops.weight_unpack_grad(dwp, gw, None, Cout, Cin, k * k, cin_p, False)
+    torch.cuda.synchronize()
+    assert rel(gw, gw_ref) < 1e-3, rel(gw, gw_ref)
+    if cin_p > Cin:      # padded input channels must receive exactly zero
+        pad_cols = dwp.view(Cout, k * k, cin_p)[:, :, Cin:]
+        assert float(pad_cols.abs().max()) == 0
 
 
 def test_conv_tc_large_matches_simt():
@@ -100,3 +113,17 @@ def test_conv_tc_large_matches_simt():
     torch.cuda.synchronize()
     ms = t0.elapsed_time(t1) / 5
     print(f"tc conv 296->128 @192x416 B=2: {ms:.3f} ms, {2*B*H*W*Cout*9*Cin/ms/1e9:.1f} TFLOP/s")
+    dy = (torch.randn(B, H, W, Cout, device=d) * 0.5).to(BF)
+    dw1 = torch.zeros(Cout, 9 * Cin, device=d)
+    dw2 = torch.zeros(Cout, 9 * Cin, device=d)
+    ops.conv_wgrad(ops.make_desc(xb, dy, Cin, Cout, 3, 3, 1, 1), xb, dy, dw1, use_tc=True)
+    ops.conv_wgrad(ops.make_desc(xb, dy, Cin, Cout, 3, 3, 1, 1), xb, dy, dw2)
+    torch.cuda.synchronize()
+    assert rel(dw1, dw2) < 1e-4, rel(dw1, dw2)
+    t0.record()
+    for _ in range(5):
+        ops.conv_wgrad(ops.make_desc(xb, dy, Cin, Cout, 3, 3, 1, 1), xb, dy, dw1, use_tc=True)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / 5
+    print(f"tc wgrad 296->128 @192x416 B=2: {ms:.3f} ms, {2*B*H*W*Cout*9*Cin/ms/1e9:.1f} TFLOP/s")
