@@ -146,7 +146,9 @@ __global__ void __launch_bounds__(256) diffgradnorm_kernel(const crd_opt_tensor*
                                                            const crd_opt_chunk* __restrict__ chunks,
                                                            const float* __restrict__ sumsq,
                                                            const float* __restrict__ egn_in, float* egn_out,
-                                                           float step_size, float beta1, float beta2, float eps) {
+                                                           const float* __restrict__ step_size_p, float beta1,
+                                                           float beta2, float eps) {
+  const float step_size = step_size_p[0];
   const crd_opt_chunk ck = chunks[blockIdx.x];
   const crd_opt_tensor t = table[ck.tensor];
   long long end = ck.start + CRD_OPT_CHUNK;
@@ -220,8 +222,9 @@ extern "C" int crd_mt_sumsq(const crd_opt_tensor* table, const crd_opt_chunk* ch
   return 0;
 }
 extern "C" int crd_diffgradnorm_update(const crd_opt_tensor* table, const crd_opt_chunk* chunks, int nchunks,
-                                       const float* sumsq, const float* egn_in, float* egn_out, float step_size,
-                                       float beta1, float beta2, float eps, crd_stream_t stream) {
+                                       const float* sumsq, const float* egn_in, float* egn_out,
+                                       const float* step_size, float beta1, float beta2, float eps,
+                                       crd_stream_t stream) {
   if (nchunks == 0) return 0;
   diffgradnorm_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(table, chunks, sumsq, egn_in, egn_out, step_size,
                                                                  beta1, beta2, eps);

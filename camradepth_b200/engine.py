@@ -85,6 +85,7 @@ class Engine:
         # optional CUDA-event timing of selected conv launches: {(kind, weight name): [(ev0, ev1), ...]}
         self.timed = None
         self._grad_epoch = 0
+        self._flat_own = None
 
     def _timed(self, kind, name):
         if self.timed is None or (kind, name) not in self.timed:
@@ -641,7 +642,29 @@ class Engine:
         self.bwd_arena.reset()
         sizes = [self.P[n].numel() for n in self.names]
         total = sum(sizes)
-        flat = torch.zeros(total, dtype=f32, device=self.device) if flat_grad is None else flat_grad
+        if flat_grad is not None:
+            flat = flat_grad
+        else:
+            # One persistent flat buffer (stable addresses: optimizer tables and CUDA graphs stay valid).  If the
+            # caller still holds gradients that alias it (no zero_grad(set_to_none=True) since the last
+            # backward, i.e. gradient accumulation), a fresh buffer is used and autograd accumulates into theirs.
+            own = self._flat_own
+            aliased = own is None or own.numel() != total or own.device != self.device
+            if not aliased:
+                lo, hi = own.data_ptr(), own.data_ptr() + own.numel() * 4
+                for p_ in (self.P[self.names[0]], self.P[self.names[-1]], self.P[self.names[len(self.names) // 2]]):
+                    if p_.grad is not None and lo <= p_.grad.data_ptr() < hi:
+                        aliased = True
+                        break
+                if aliased:
+                    own = None
+            if own is None or own.numel() != total or own.device != self.device:
+                flat = torch.zeros(total, dtype=f32, device=self.device)
+                if self._flat_own is None or self._flat_own.numel() != total or self._flat_own.device != self.device:
+                    self._flat_own = flat
+            else:
+                flat = own
+                flat.zero_()
         self.pg = {}
         off = 0
         self.pg_offsets = {}

@@ -286,5 +286,5 @@ def mt_sumsq(table, chunks, nchunks, sumsq):
 
 
 def diffgradnorm_update(table, chunks, nchunks, sumsq, egn_in, egn_out, step_size, beta1, beta2, eps):
-    K.crd_diffgradnorm_update(P(table), P(chunks), nchunks, P(sumsq), P(egn_in), P(egn_out), step_size, beta1,
+    K.crd_diffgradnorm_update(P(table), P(chunks), nchunks, P(sumsq), P(egn_in), P(egn_out), P(step_size), beta1,
                               beta2, eps, stream())

@@ -45,6 +45,31 @@ class diffGradNorm(Optimizer):
             ck[i, 1] = start
         return table, ck
 
+    @staticmethod
+    def _step_size(group, step_no):
+        beta1, beta2 = group['betas']
+        bc1 = 1 - beta1 ** step_no
+        bc2 = 1 - beta2 ** step_no
+        return group['lr'] * math.sqrt(bc2) / (bc1 + 1e-8)       # diffGradNorm.py:97-108
+
+    @torch.no_grad()
+    def advance_for_replay(self):
+        """Host-side part of a step whose device work is replayed from a CUDA graph: bump the step counters
+        and refresh the device-resident step size (lr schedule + bias corrections)."""
+        for gi, group in enumerate(self.param_groups):
+            ent = self._tables.get(gi)
+            if ent is None:
+                continue
+            step_no = None
+            for p in group['params']:
+                st = self.state.get(p)
+                if st:
+                    st['step'] += 1
+                    step_no = st['step']
+            if step_no is not None:
+                ent[7].fill_(self._step_size(group, step_no))
+        bump_weight_epoch()
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -72,6 +97,7 @@ class diffGradNorm(Optimizer):
                     st['exp_avg_sq'] = torch.zeros_like(p.data)
                     st['previous_grad'] = torch.zeros_like(p.data)
                     st['exp_grad_norm'] = torch.zeros((), dtype=torch.float32, device=dev)
+                    st['_slot'] = None
                 st['step'] += 1
                 by_step.setdefault(st['step'], []).append(p)
             beta1, beta2 = group['betas']
@@ -85,19 +111,30 @@ class diffGradNorm(Optimizer):
                              self.state[p]['exp_avg_sq'].data_ptr(), self.state[p]['previous_grad'].data_ptr())
                             for p, g in zip(plist, grads)]
                     table, ck = self.build_tables(ptrs, [p.numel() for p in plist], dev)
-                    ent = (key, torch.from_numpy(table).to(dev), torch.from_numpy(ck).to(dev), ck.shape[0])
+                    T = len(plist)
+                    # per-tensor exp_grad_norm lives in one persistent ping-pong buffer; state entries are views
+                    egn = torch.stack([self.state[p]['exp_grad_norm'].reshape(()) for p in plist]).contiguous()
+                    pp = torch.stack([egn, torch.zeros_like(egn)]).contiguous()
+                    ent = [key, torch.from_numpy(table).to(dev), torch.from_numpy(ck).to(dev), ck.shape[0], pp, 0,
+                           torch.zeros(T, dtype=torch.float32, device=dev),
+                           torch.zeros(1, dtype=torch.float32, device=dev)]
                     self._tables[gi] = ent
-                _, table_d, ck_d, nchunks = ent
-                T = len(plist)
-                sumsq = torch.zeros(T, dtype=torch.float32, device=dev)
-                egn_in = torch.stack([self.state[p]['exp_grad_norm'] for p in plist]).contiguous()
-                egn_out = torch.empty_like(egn_in)
+                _, table_d, ck_d, nchunks, pp, cur, sumsq, hyper = ent
+                sumsq.zero_()
+                egn_in, egn_out = pp[cur], pp[1 - cur]
                 ops.mt_sumsq(table_d, ck_d, nchunks, sumsq)
-                bc1 = 1 - beta1 ** step_no
-                bc2 = 1 - beta2 ** step_no
-                step_size = group['lr'] * math.sqrt(bc2) / (bc1 + 1e-8)
-                ops.diffgradnorm_update(table_d, ck_d, nchunks, sumsq, egn_in, egn_out, float(step_size),
+                if not torch.cuda.is_current_stream_capturing():
+                    # the step size lives in a device scalar so a captured step can be replayed with fresh
+                    # bias corrections (see advance_for_replay)
+                    hyper.fill_(self._step_size(group, step_no))
+                ops.diffgradnorm_update(table_d, ck_d, nchunks, sumsq, egn_in, egn_out, hyper,
                                         float(beta1), float(beta2), float(group['eps']))
+                if torch.cuda.is_current_stream_capturing():
+                    # a replayed graph must read and write the same exp_grad_norm buffer every time
+                    pp[cur].copy_(pp[1 - cur])
+                    egn_out = pp[cur]
+                else:
+                    ent[5] = 1 - cur
                 for i, p in enumerate(plist):
                     self.state[p]['exp_grad_norm'] = egn_out[i]
         bump_weight_epoch()

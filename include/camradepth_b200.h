@@ -193,10 +193,11 @@ typedef struct { int tensor; int pad; long long start; } crd_opt_chunk;   /* chu
 #define CRD_OPT_CHUNK 16384
 CRD_API int crd_mt_sumsq(const crd_opt_tensor* table, const crd_opt_chunk* chunks, int nchunks, float* sumsq,
                  crd_stream_t stream);
-/* step_size = lr*sqrt(1-beta2^t)/((1-beta1^t)+1e-8) (diffGradNorm.py:108); egn_in/egn_out: per-tensor
- * exp_grad_norm before/after (ping-pong so every chunk of a tensor sees the same input) */
+/* step_size[0] (DEVICE scalar, so a CUDA-graph replay sees fresh values) = lr*sqrt(1-beta2^t)/((1-beta1^t)+1e-8)
+ * (diffGradNorm.py:108); egn_in/egn_out: per-tensor exp_grad_norm before/after (ping-pong so every chunk of a
+ * tensor sees the same input) */
 CRD_API int crd_diffgradnorm_update(const crd_opt_tensor* table, const crd_opt_chunk* chunks, int nchunks,
-                            const float* sumsq, const float* egn_in, float* egn_out, float step_size,
+                            const float* sumsq, const float* egn_in, float* egn_out, const float* step_size,
                             float beta1, float beta2, float eps, crd_stream_t stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,64 @@
+"""CUDA-graph replay of the whole training step must equal eager execution (GPU)."""
+import pytest
+import torch
+
+from tests.test_gpu_ops import rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(seed):
+    import camradepth_b200 as C
+    from camradepth_b200.synthetic import make_batch
+    C.set_model("base")
+    torch.manual_seed(seed)
+    m = C.CamRaDepth(precision="bf16").cuda().eval()      # eval: no stochastic masks, so runs are comparable
+    opt = C.diffGradNorm(m.parameters(), lr=1e-3)
+    crit = C.MaskedSmoothL1Loss()
+    b = {k: v.cuda() for k, v in make_batch(2, 64, 96, seed=4).items()}
+
+    def step(bb):
+        pred = m(bb["image"])
+        loss = crit(pred["depth"]["final_depth"], bb["gt_final"]) + crit(pred["depth"]["intermediate_depths"][-1], bb["gt_s4"])
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+    return m, opt, step, b
+
+
+def test_graphed_train_step_matches_eager():
+    from camradepth_b200.graphs import GraphedTrainStep
+    m1, o1, step1, b = _setup(0)
+    m2, o2, step2, _ = _setup(0)
+    for _ in range(3):
+        step1(b)
+    l_eager = [float(step1(b)) for _ in range(3)]
+    for _ in range(3):
+        step2(b)
+    g = GraphedTrainStep(step2, b, warmup=0)       # capture performs the 4th step
+    l_graph = [float(g.loss)]
+    for _ in range(2):
+        o2.advance_for_replay()
+        l_graph.append(float(g(b)))
+    torch.cuda.synchronize()
+    assert abs(l_eager[0] - l_graph[0]) < 2e-3 * abs(l_eager[0])
+    assert l_graph[2] != l_graph[0]                  # parameters really move between replays
+    for a, c in zip(l_eager, l_graph):
+        assert abs(a - c) < 2e-2 * abs(a), (l_eager, l_graph)
+    p1 = torch.cat([p.detach().flatten() for p in m1.parameters()])
+    p2 = torch.cat([p.detach().flatten() for p in m2.parameters()])
+    assert rel(p2, p1) < 1e-3
+    assert o1.state[next(iter(m1.parameters()))]["step"] == o2.state[next(iter(m2.parameters()))]["step"]
+
+
+def test_graphed_inference_matches_eager():
+    from camradepth_b200.graphs import GraphedInference
+    m, _, _, b = _setup(1)
+    with torch.no_grad():
+        ref = m(b["image"])["depth"]["final_depth"].clone()
+    g = GraphedInference(m, b["image"])
+    out = g(b["image"])["depth"]["final_depth"]
+    assert rel(out, ref) < 5e-3
+    out2 = g(b["image"] * 0.5)["depth"]["final_depth"]
+    assert rel(out2, ref) > 1e-3
