@@ -54,6 +54,22 @@ inline ReduceLaunch plan_reduce(int B, long long N, int C) {
 }
 
 
+// streaming (non-reducing) kernels with the same (cvec, rows) thread mapping: more, smaller blocks
+inline ReduceLaunch plan_stream(int B, long long N, int C) {
+  ReduceLaunch r;
+  int cvec = C / 8;
+  int rows = 256 / cvec; if (rows < 1) rows = 1; if (rows > 32) rows = 32;
+  long long blocks_per_b = (148LL * 16 + B - 1) / B;
+  long long min_ppb = rows * 8;
+  long long ppb = (N + blocks_per_b - 1) / blocks_per_b;
+  if (ppb < min_ppb) ppb = min_ppb;
+  r.ppb = ppb;
+  r.grid = dim3((unsigned)((N + ppb - 1) / ppb), B);
+  r.block = dim3(cvec, rows);
+  r.smem = 0;
+  return r;
+}
+
 inline int ew_blocks(long long total) {
   long long b = (total + 255) / 256;
   long long cap = 148LL * 16;

@@ -302,7 +302,8 @@ __global__ void weight_pack_kernel(const float* __restrict__ w, T* __restrict__ 
     const int co = (int)(i / ((long long)taps * Cin));
     const int cm = map ? map[ci] : ci;
     const long long o = mode == 0 ? ((long long)co * taps + tap) * Cin_p + cm
-                                  : ((long long)cm * taps + tap) * Cout_p + co;
+                      : mode == 1 ? ((long long)cm * taps + tap) * Cout_p + co
+                                  : ((long long)tap * Cin_p + cm) * Cout_p + co;
     dst[o] = from_f<T>(w[i]);
   }
 }
@@ -318,6 +319,77 @@ __global__ void weight_unpack_grad_kernel(const float* __restrict__ dwp, float* 
     const int cm = map ? map[ci] : ci;
     const float v = dwp[((long long)co * taps + tap) * Cin_p + cm];
     grad[i] = accumulate ? grad[i] + v : v;
+  }
+}
+
+// ------------------------------------------------------------------ strided convs as GEMMs
+// col[m][(kh*KW+kw)*Cin + c] = x[b, oh*stride-pad+kh, ow*stride-pad+kw, c]   (zero outside the image)
+template <typename T>
+__global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ col, int B, int H, int W, int Cin, int ldx,
+                              int Ho, int Wo, int KH, int KW, int stride, int pad) {
+  const int cvec = Cin / 8;
+  const int taps = KH * KW;
+  const long long total = (long long)B * Ho * Wo * taps * cvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    long long t = i / cvec;
+    const int tap = (int)(t % taps);
+    const long long m = t / taps;
+    const int ow = (int)(m % Wo);
+    const int oh = (int)((m / Wo) % Ho);
+    const int b = (int)(m / ((long long)Wo * Ho));
+    const int kh = tap / KW, kw = tap - kh * KW;
+    const int ih = oh * stride - pad + kh, iw = ow * stride - pad + kw;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = 0.f;
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) load8(x + (((long long)b * H + ih) * W + iw) * ldx + cv * 8, v);
+    store8(col + (m * taps + tap) * Cin + cv * 8, v);
+  }
+}
+// dx[b,ih,iw,c] (+)= sum over the (oh,ow,kh,kw) that read it of dcol[m][(kh*KW+kw)*Cin + c]  (gather form)
+template <typename T>
+__global__ void col2im_kernel(const T* __restrict__ dcol, T* __restrict__ dx, int accumulate, int B, int H, int W,
+                              int Cin, int lddx, int Ho, int Wo, int KH, int KW, int stride, int pad) {
+  const int cvec = Cin / 8;
+  const int taps = KH * KW;
+  const long long total = (long long)B * H * W * cvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    long long pix = i / cvec;
+    const int iw = (int)(pix % W);
+    const int ih = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+    for (int kh = 0; kh < KH; kh++) {
+      const int th = ih + pad - kh;
+      if (th < 0 || th % stride) continue;
+      const int oh = th / stride;
+      if (oh >= Ho) continue;
+      for (int kw = 0; kw < KW; kw++) {
+        const int tw = iw + pad - kw;
+        if (tw < 0 || tw % stride) continue;
+        const int ow = tw / stride;
+        if (ow >= Wo) continue;
+        const long long m = ((long long)b * Ho + oh) * Wo + ow;
+        float g[8];
+        load8(dcol + (m * taps + kh * KW + kw) * Cin + cv * 8, g);
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] += g[j];
+      }
+    }
+    T* o = dx + pix * lddx + cv * 8;
+    if (accumulate) {
+      float old[8];
+      load8(o, old);
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[j] += old[j];
+    }
+    store8(o, acc);
   }
 }
 
@@ -452,6 +524,26 @@ extern "C" int crd_weight_unpack_grad(const float* dwp, float* grad, const int* 
   if (total == 0) return 0;
   weight_unpack_grad_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(dwp, grad, map, Cout, Cin, taps,
                                                                                Cin_p, accumulate);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_im2col(const void* x, void* col, int dtype, int B, int H, int W, int Cin, int ldx, int Ho, int Wo,
+                          int KH, int KW, int stride, int pad, crd_stream_t stream) {
+  CRD_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0);
+  const long long total = (long long)B * Ho * Wo * KH * KW * (Cin / 8);
+  if (total == 0) return 0;
+  CRD_DISPATCH_1(dtype, T, im2col_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)x, (T*)col, B, H, W, Cin, ldx, Ho, Wo, KH, KW, stride, pad));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_col2im(const void* dcol, void* dx, int dtype, int accumulate, int B, int H, int W, int Cin,
+                          int lddx, int Ho, int Wo, int KH, int KW, int stride, int pad, crd_stream_t stream) {
+  CRD_REQUIRE(Cin % 8 == 0 && lddx % 8 == 0);
+  const long long total = (long long)B * H * W * (Cin / 8);
+  if (total == 0) return 0;
+  CRD_DISPATCH_1(dtype, T, col2im_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)dcol, (T*)dx, accumulate, B, H, W, Cin, lddx, Ho, Wo, KH, KW, stride, pad));
   CRD_LAUNCH_CHECK();
   return 0;
 }

@@ -9,27 +9,34 @@
 namespace {
 
 // ------------------------------------------------------------------ depthwise 3x3
+// blockDim = (C/8, rows), grid = (pixel chunks, B): each thread keeps the 9x8 filter taps, the GroupNorm affine
+// and the bias of its 8 channels in registers and streams over pixels (16-byte loads, neighbours hit L1/L2).
 template <typename T>
-__global__ void dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ ab,
-                                  const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ y,
-                                  int B, int H, int W, int C) {
-  const int cvec = C / 8;
-  const long long total = (long long)B * H * W * cvec;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % cvec);
-    long long pix = i / cvec;
-    const int ww = (int)(pix % W);
-    const int hh = (int)((pix / W) % H);
-    const int b = (int)(pix / ((long long)W * H));
-    const int c = cv * 8;
-    float a[8], sh[8], acc[8];
+__global__ void __launch_bounds__(256) dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ ab,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         T* __restrict__ y, int B, int H, int W, int C,
+                                                         long long ppb) {
+  const int c = threadIdx.x * 8, ry = threadIdx.y, rows = blockDim.y;
+  const int b = blockIdx.y;
+  const long long N = (long long)H * W;
+  long long p0 = (long long)blockIdx.x * ppb, p1 = p0 + ppb;
+  if (p1 > N) p1 = N;
+  float wt[9][8], a[8], sh[8], bs[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      a[j] = ab[((long long)b * C + c + j) * 2];
-      sh[j] = ab[((long long)b * C + c + j) * 2 + 1];
-      acc[j] = bias ? bias[c + j] : 0.f;
-    }
+  for (int j = 0; j < 8; j++) {
+    a[j] = ab[((long long)b * C + c + j) * 2];
+    sh[j] = ab[((long long)b * C + c + j) * 2 + 1];
+    bs[j] = bias ? bias[c + j] : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; t++) wt[t][j] = w[(c + j) * 9 + t];
+  }
+  const T* xb = x + (long long)b * N * C + c;
+  T* yb = y + (long long)b * N * C + c;
+  for (long long p = p0 + ry; p < p1; p += rows) {
+    const int hh = (int)(p / W), ww = (int)(p - (long long)hh * W);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = bs[j];
 #pragma unroll
     for (int dh = -1; dh <= 1; dh++) {
       const int h2 = hh + dh;
@@ -39,29 +46,33 @@ __global__ void dwconv_fwd_kernel(const T* __restrict__ x, const float* __restri
         const int w2 = ww + dw;
         if (w2 < 0 || w2 >= W) continue;
         float v[8];
-        load8(x + (((long long)b * H + h2) * W + w2) * C + c, v);
-        const int tap = (dh + 1) * 3 + (dw + 1);
+        load8(xb + ((long long)h2 * W + w2) * C, v);
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[j] = fmaf(w[(c + j) * 9 + tap], fmaf(a[j], v[j], sh[j]), acc[j]);
+        for (int j = 0; j < 8; j++) acc[j] = fmaf(wt[(dh + 1) * 3 + (dw + 1)][j], fmaf(a[j], v[j], sh[j]), acc[j]);
       }
     }
-    store8(y + pix * C + c, acc);
+    store8(yb + p * C, acc);
   }
 }
 
 template <typename T>
-__global__ void dwconv_bwd_input_kernel(const T* __restrict__ dy, const float* __restrict__ w,
-                                        T* __restrict__ dxn, int B, int H, int W, int C) {
-  const int cvec = C / 8;
-  const long long total = (long long)B * H * W * cvec;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % cvec);
-    long long pix = i / cvec;
-    const int ww = (int)(pix % W);
-    const int hh = (int)((pix / W) % H);
-    const int b = (int)(pix / ((long long)W * H));
-    const int c = cv * 8;
+__global__ void __launch_bounds__(256) dwconv_bwd_input_kernel(const T* __restrict__ dy, const float* __restrict__ w,
+                                                               T* __restrict__ dxn, int B, int H, int W, int C,
+                                                               long long ppb) {
+  const int c = threadIdx.x * 8, ry = threadIdx.y, rows = blockDim.y;
+  const int b = blockIdx.y;
+  const long long N = (long long)H * W;
+  long long p0 = (long long)blockIdx.x * ppb, p1 = p0 + ppb;
+  if (p1 > N) p1 = N;
+  float wt[9][8];
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+#pragma unroll
+    for (int t = 0; t < 9; t++) wt[t][j] = w[(c + j) * 9 + t];
+  const T* gb = dy + (long long)b * N * C + c;
+  T* ob = dxn + (long long)b * N * C + c;
+  for (long long p = p0 + ry; p < p1; p += rows) {
+    const int hh = (int)(p / W), ww = (int)(p - (long long)hh * W);
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[j] = 0.f;
@@ -74,13 +85,12 @@ __global__ void dwconv_bwd_input_kernel(const T* __restrict__ dy, const float* _
         const int w2 = ww - dw;
         if (w2 < 0 || w2 >= W) continue;
         float g[8];
-        load8(dy + (((long long)b * H + h2) * W + w2) * C + c, g);
-        const int tap = (dh + 1) * 3 + (dw + 1);
+        load8(gb + ((long long)h2 * W + w2) * C, g);
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[j] = fmaf(w[(c + j) * 9 + tap], g[j], acc[j]);
+        for (int j = 0; j < 8; j++) acc[j] = fmaf(wt[(dh + 1) * 3 + (dw + 1)][j], g[j], acc[j]);
       }
     }
-    store8(dxn + pix * C + c, acc);
+    store8(ob + p * C, acc);
   }
 }
 
@@ -382,21 +392,21 @@ __global__ void add_f32_kernel(float* __restrict__ dst, const T* __restrict__ sr
 
 extern "C" int crd_dwconv3x3_fwd(const void* x, int dtype, const float* ab, const float* w, const float* bias,
                                  void* y, int B, int H, int W, int C, crd_stream_t stream) {
-  CRD_REQUIRE(C % 8 == 0);
-  const long long total = (long long)B * H * W * (C / 8);
-  if (total == 0) return 0;
-  CRD_DISPATCH_1(dtype, T, dwconv_fwd_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
-                               (const T*)x, ab, w, bias, (T*)y, B, H, W, C));
+  CRD_REQUIRE(C % 8 == 0 && C / 8 <= 256);
+  if ((long long)B * H * W == 0) return 0;
+  ReduceLaunch r = plan_stream(B, (long long)H * W, C);
+  CRD_DISPATCH_1(dtype, T, dwconv_fwd_kernel<T><<<r.grid, r.block, 0, (cudaStream_t)stream>>>(
+                               (const T*)x, ab, w, bias, (T*)y, B, H, W, C, r.ppb));
   CRD_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int crd_dwconv3x3_bwd_input(const void* dy, int dtype, const float* w, void* dxn, int B, int H, int W,
                                        int C, crd_stream_t stream) {
-  CRD_REQUIRE(C % 8 == 0);
-  const long long total = (long long)B * H * W * (C / 8);
-  if (total == 0) return 0;
-  CRD_DISPATCH_1(dtype, T, dwconv_bwd_input_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
-                               (const T*)dy, w, (T*)dxn, B, H, W, C));
+  CRD_REQUIRE(C % 8 == 0 && C / 8 <= 256);
+  if ((long long)B * H * W == 0) return 0;
+  ReduceLaunch r = plan_stream(B, (long long)H * W, C);
+  CRD_DISPATCH_1(dtype, T, dwconv_bwd_input_kernel<T><<<r.grid, r.block, 0, (cudaStream_t)stream>>>(
+                               (const T*)dy, w, (T*)dxn, B, H, W, C, r.ppb));
   CRD_LAUNCH_CHECK();
   return 0;
 }

@@ -24,29 +24,40 @@ __global__ void gn_finalize_kernel(const float* __restrict__ sums, const float* 
                                    const float* __restrict__ beta, float* __restrict__ ab,
                                    float* __restrict__ mean_rstd, float* __restrict__ xbar, int B, int C, int G,
                                    long long N, float eps) {
+  extern __shared__ float gs[];             // [G][2]: mean, rstd
   const int b = blockIdx.x;
   const int cpg = C / G;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int g = warp; g < G; g += nw) {      // one warp per group
     double s = 0.0, ss = 0.0;
-    for (int j = 0; j < cpg; j++) {
+    for (int j = lane; j < cpg; j += 32) {
       const float* p = sums + ((long long)b * C + g * cpg + j) * 2;
       s += (double)p[0]; ss += (double)p[1];
     }
-    const double cnt = (double)cpg * (double)N;
-    const double mean = s / cnt;
-    double var = ss / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float a = gamma[c] * rstd;
-    const float bb = beta[c] - (float)mean * a;
-    ab[((long long)b * C + c) * 2 + 0] = a;
-    ab[((long long)b * C + c) * 2 + 1] = bb;
-    if (xbar) xbar[(long long)b * C + c] = a * (sums[((long long)b * C + c) * 2] / (float)N) + bb;
-    if (c == g * cpg) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0) {
+      const double cnt = (double)cpg * (double)N;
+      const double mean = s / cnt;
+      double var = ss / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+      gs[2 * g] = (float)mean; gs[2 * g + 1] = rstd;
       mean_rstd[((long long)b * G + g) * 2 + 0] = (float)mean;
       mean_rstd[((long long)b * G + g) * 2 + 1] = rstd;
     }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float a = gamma[c] * gs[2 * g + 1];
+    const float bb = beta[c] - gs[2 * g] * a;
+    ab[((long long)b * C + c) * 2 + 0] = a;
+    ab[((long long)b * C + c) * 2 + 1] = bb;
+    if (xbar) xbar[(long long)b * C + c] = a * (sums[((long long)b * C + c) * 2] / (float)N) + bb;
   }
 }
 
@@ -64,26 +75,29 @@ __device__ __forceinline__ float act_bwd(float z, int act) {
 template <typename TI, typename TO>
 __global__ void affine_act_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* __restrict__ ab,
                                   const float* __restrict__ post, int act, int B, long long N, int C, int ldx,
-                                  int ldy) {
-  const int cvec = C / 8;
-  const long long total = (long long)B * N * cvec;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % cvec);
-    const long long pix = i / cvec;
-    const int b = (int)(pix / N);
-    const int c = cv * 8;
-    float v[8];
-    load8(x + pix * ldx + c, v);
-    const float* abp = ab + ((long long)b * C + c) * 2;
+                                  int ldy, long long ppb) {
+  // blockDim = (C/8, rows); each thread keeps the per-(b,c) affine of its 8 channels in registers and
+  // streams over the block's pixel range (coalesced 16-byte accesses, no per-pixel parameter loads)
+  const int c = threadIdx.x * 8, ry = threadIdx.y, rows = blockDim.y;
+  const int b = blockIdx.y;
+  long long p0 = (long long)blockIdx.x * ppb, p1 = p0 + ppb;
+  if (p1 > N) p1 = N;
+  float a[8], sh[8], ps[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      float z = fmaf(abp[2 * j], v[j], abp[2 * j + 1]);
-      z = act_fwd(z, act);
-      if (post) z *= post[(long long)b * C + c + j];
-      v[j] = z;
-    }
-    store8(y + pix * ldy + c, v);
+  for (int j = 0; j < 8; j++) {
+    a[j] = ab[((long long)b * C + c + j) * 2];
+    sh[j] = ab[((long long)b * C + c + j) * 2 + 1];
+    ps[j] = post ? post[(long long)b * C + c + j] : 1.f;
+  }
+  const TI* xb = x + (long long)b * N * ldx + c;
+  TO* yb = y + (long long)b * N * ldy + c;
+#pragma unroll 2
+  for (long long p = p0 + ry; p < p1; p += rows) {
+    float v[8];
+    load8(xb + p * ldx, v);
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = act_fwd(fmaf(a[j], v[j], sh[j]), act) * ps[j];
+    store8(yb + p * ldy, v);
   }
 }
 
@@ -92,18 +106,24 @@ __global__ void gnact_bwd_reduce_kernel(const TD* __restrict__ dy, const TX* __r
                                         const float* __restrict__ ab, const float* __restrict__ post,
                                         const float* __restrict__ addbc, int act, float* pq, int B, long long N,
                                         int C, int lddy, int ldx, long long ppb) {
+  const int c0 = threadIdx.x * 8, b0 = blockIdx.y;
+  float a[8], sh[8], ps[8], ad[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    a[j] = ab[((long long)b0 * C + c0 + j) * 2];
+    sh[j] = ab[((long long)b0 * C + c0 + j) * 2 + 1];
+    ps[j] = post ? post[(long long)b0 * C + c0 + j] : 1.f;
+    ad[j] = addbc ? addbc[(long long)b0 * C + c0 + j] : 0.f;
+  }
   chan_reduce2([&](int b, long long p, int c, float (&s0)[8], float (&s1)[8]) {
     float g[8], v[8];
     const long long pix = (long long)b * N + p;
     load8(dy + pix * lddy + c, g);
     load8(x + pix * ldx + c, v);
-    const float* abp = ab + ((long long)b * C + c) * 2;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      float dz = g[j];
-      if (addbc) dz += addbc[(long long)b * C + c + j];
-      if (post) dz *= post[(long long)b * C + c + j];
-      if (act != CRD_ACT_NONE) dz *= act_bwd(fmaf(abp[2 * j], v[j], abp[2 * j + 1]), act);
+      float dz = (g[j] + ad[j]) * ps[j];
+      if (act != CRD_ACT_NONE) dz *= act_bwd(fmaf(a[j], v[j], sh[j]), act);
       s0[j] += dz;
       s1[j] = fmaf(dz, v[j], s1[j]);
     }
@@ -113,27 +133,42 @@ __global__ void gnact_bwd_reduce_kernel(const TD* __restrict__ dy, const TX* __r
 __global__ void gn_bwd_finalize_kernel(const float* __restrict__ pq, const float* __restrict__ mean_rstd,
                                        const float* __restrict__ gamma, float* __restrict__ coef,
                                        float* dgamma, float* dbeta, int B, int C, int G, long long N) {
+  extern __shared__ float gs[];             // [G][2]: m1, m2
   const int b = blockIdx.x;
   const int cpg = C / G;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int g = warp; g < G; g += nw) {
     const float mu = mean_rstd[((long long)b * G + g) * 2 + 0];
     const float r = mean_rstd[((long long)b * G + g) * 2 + 1];
     double t1 = 0.0, t2 = 0.0;
-    for (int j = 0; j < cpg; j++) {
+    for (int j = lane; j < cpg; j += 32) {
       const int cc = g * cpg + j;
       const float* p = pq + ((long long)b * C + cc) * 2;
       const double ga = (double)gamma[cc];
       t1 += ga * (double)p[0];
       t2 += ga * ((double)p[1] - (double)mu * (double)p[0]);
     }
-    const double m = (double)cpg * (double)N;
-    const double m1 = t1 / m;
-    const double m2 = (double)r * t2 / m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+      t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+    }
+    if (lane == 0) {
+      const double m = (double)cpg * (double)N;
+      gs[2 * g] = (float)(t1 / m);
+      gs[2 * g + 1] = (float)((double)r * t2 / m);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mu = mean_rstd[((long long)b * G + g) * 2 + 0];
+    const float r = mean_rstd[((long long)b * G + g) * 2 + 1];
+    const float m1 = gs[2 * g], m2 = gs[2 * g + 1];
     float* cf = coef + ((long long)b * C + c) * 3;
     cf[0] = r * gamma[c];
-    cf[1] = (float)(-(double)r * (double)r * m2);
-    cf[2] = (float)(-(double)r * m1 + (double)r * (double)r * m2 * (double)mu);
+    cf[1] = -r * r * m2;
+    cf[2] = -r * m1 + r * r * m2 * mu;
     const float* p = pq + ((long long)b * C + c) * 2;
     if (dgamma) atomicAdd(dgamma + c, r * (p[1] - mu * p[0]));
     if (dbeta) atomicAdd(dbeta + c, p[0]);
@@ -145,31 +180,40 @@ __global__ void gnact_bwd_apply_kernel(const TD* __restrict__ dy, const TX* __re
                                        const float* __restrict__ ab, const float* __restrict__ post,
                                        const float* __restrict__ addbc, int act, const float* __restrict__ coef,
                                        TO* __restrict__ dx, int accumulate, int B, long long N, int C, int lddy,
-                                       int ldx, int lddx) {
-  const int cvec = C / 8;
-  const long long total = (long long)B * N * cvec;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % cvec);
-    const long long pix = i / cvec;
-    const int b = (int)(pix / N);
-    const int c = cv * 8;
+                                       int ldx, int lddx, long long ppb) {
+  const int c = threadIdx.x * 8, ry = threadIdx.y, rows = blockDim.y;
+  const int b = blockIdx.y;
+  long long p0 = (long long)blockIdx.x * ppb, p1 = p0 + ppb;
+  if (p1 > N) p1 = N;
+  float a[8], sh[8], ps[8], ad[8], cA[8], cB[8], cC[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const long long bc = (long long)b * C + c + j;
+    a[j] = ab[bc * 2];
+    sh[j] = ab[bc * 2 + 1];
+    ps[j] = post ? post[bc] : 1.f;
+    ad[j] = addbc ? addbc[bc] : 0.f;
+    cA[j] = coef[bc * 3];
+    cB[j] = coef[bc * 3 + 1];
+    cC[j] = coef[bc * 3 + 2];
+  }
+  const TD* dyb = dy + (long long)b * N * lddy + c;
+  const TX* xb = x + (long long)b * N * ldx + c;
+  TO* dxb = dx + (long long)b * N * lddx + c;
+#pragma unroll 2
+  for (long long p = p0 + ry; p < p1; p += rows) {
     float g[8], v[8], o[8];
-    load8(dy + pix * lddy + c, g);
-    load8(x + pix * ldx + c, v);
-    if (accumulate) load8(dx + pix * lddx + c, o);
-    const float* abp = ab + ((long long)b * C + c) * 2;
-    const float* cf = coef + ((long long)b * C + c) * 3;
+    load8(dyb + p * lddy, g);
+    load8(xb + p * ldx, v);
+    if (accumulate) load8(dxb + p * lddx, o);
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      float dz = g[j];
-      if (addbc) dz += addbc[(long long)b * C + c + j];
-      if (post) dz *= post[(long long)b * C + c + j];
-      if (act != CRD_ACT_NONE) dz *= act_bwd(fmaf(abp[2 * j], v[j], abp[2 * j + 1]), act);
-      float r = fmaf(cf[3 * j], dz, fmaf(cf[3 * j + 1], v[j], cf[3 * j + 2]));
+      float dz = (g[j] + ad[j]) * ps[j];
+      if (act != CRD_ACT_NONE) dz *= act_bwd(fmaf(a[j], v[j], sh[j]), act);
+      const float r = fmaf(cA[j], dz, fmaf(cB[j], v[j], cC[j]));
       o[j] = accumulate ? o[j] + r : r;
     }
-    store8(dx + pix * lddx + c, o);
+    store8(dxb + p * lddx, o);
   }
 }
 
@@ -191,7 +235,7 @@ extern "C" int crd_gn_finalize(const float* sums, const float* gamma, const floa
                                crd_stream_t stream) {
   CRD_REQUIRE(G > 0 && C % G == 0);
   if (B == 0) return 0;
-  gn_finalize_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(sums, gamma, beta, ab, mean_rstd, xbar, B, C, G, N, eps);
+  gn_finalize_kernel<<<B, 256, 2 * G * sizeof(float), (cudaStream_t)stream>>>(sums, gamma, beta, ab, mean_rstd, xbar, B, C, G, N, eps);
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -200,12 +244,12 @@ extern "C" int crd_affine_act(const void* x, int in_dtype, void* y, int out_dtyp
                               const float* post, int act, int B, long long N, int C, int ldx, int ldy,
                               crd_stream_t stream) {
   CRD_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0);
-  const long long total = (long long)B * N * (C / 8);
-  if (total == 0) return 0;
+  CRD_REQUIRE(C / 8 <= 256);
+  if ((long long)B * N == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  const int nb = ew_blocks(total);
-  CRD_DISPATCH_1(in_dtype, TI, CRD_DISPATCH_1(out_dtype, TO, affine_act_kernel<TI, TO><<<nb, 256, 0, s>>>(
-                                   (const TI*)x, (TO*)y, ab, post, act, B, N, C, ldx, ldy)));
+  ReduceLaunch r = plan_stream(B, N, C);
+  CRD_DISPATCH_1(in_dtype, TI, CRD_DISPATCH_1(out_dtype, TO, affine_act_kernel<TI, TO><<<r.grid, r.block, 0, s>>>(
+                                   (const TI*)x, (TO*)y, ab, post, act, B, N, C, ldx, ldy, r.ppb)));
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -228,7 +272,7 @@ extern "C" int crd_gn_bwd_finalize(const float* pq, const float* mean_rstd, cons
                                    crd_stream_t stream) {
   CRD_REQUIRE(G > 0 && C % G == 0);
   if (B == 0) return 0;
-  gn_bwd_finalize_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(pq, mean_rstd, gamma, coef, dgamma, dbeta, B, C, G, N);
+  gn_bwd_finalize_kernel<<<B, 256, 2 * G * sizeof(float), (cudaStream_t)stream>>>(pq, mean_rstd, gamma, coef, dgamma, dbeta, B, C, G, N);
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -238,13 +282,14 @@ extern "C" int crd_gnact_bwd_apply(const void* dy, int dy_dtype, const void* x, 
                                    int dx_dtype, int accumulate, int B, long long N, int C, int lddy, int ldx,
                                    int lddx, crd_stream_t stream) {
   CRD_REQUIRE(C % 8 == 0 && lddy % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0);
-  const long long total = (long long)B * N * (C / 8);
-  if (total == 0) return 0;
+  CRD_REQUIRE(C / 8 <= 256);
+  if ((long long)B * N == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  const int nb = ew_blocks(total);
+  ReduceLaunch r = plan_stream(B, N, C);
   CRD_DISPATCH_1(dy_dtype, TD, CRD_DISPATCH_1(x_dtype, TX, CRD_DISPATCH_1(dx_dtype, TO,
-      gnact_bwd_apply_kernel<TD, TX, TO><<<nb, 256, 0, s>>>((const TD*)dy, (const TX*)x, ab, post, addbc, act, coef,
-                                                           (TO*)dx, accumulate, B, N, C, lddy, ldx, lddx))));
+      gnact_bwd_apply_kernel<TD, TX, TO><<<r.grid, r.block, 0, s>>>((const TD*)dy, (const TX*)x, ab, post, addbc, act,
+                                                                   coef, (TO*)dx, accumulate, B, N, C, lddy, ldx,
+                                                                   lddx, r.ppb))));
   CRD_LAUNCH_CHECK();
   return 0;
 }

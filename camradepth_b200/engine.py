@@ -188,8 +188,10 @@ class Engine:
             dst = ent[0]
         elif mode == 0:
             dst = torch.zeros(L["cout"], L["taps"] * L["cin_p"], dtype=dtype, device=self.device)
-        else:
+        elif mode == 1:
             dst = torch.zeros(L["cin_p"], L["taps"] * L["cout_p"], dtype=dtype, device=self.device)
+        else:
+            dst = torch.zeros(L["taps"] * L["cin_p"], L["cout_p"], dtype=dtype, device=self.device)
         ops.weight_pack(p.detach(), dst, self._cmap(name), L["cout"], L["cin"], L["taps"], L["cin_p"], L["cout_p"],
                         mode)
         self._packs[key] = (dst, ver)
@@ -200,9 +202,23 @@ class Engine:
         return (self.tdtype == torch.bfloat16 and L["stride"] == 1 and L["k"] in (1, 3) and
                 2 * L["pad"] == L["k"] - 1 and x.dtype == torch.bfloat16)
 
+    def _gemm_route(self, L, x):
+        """strided convs (patch embeddings, spatial-reduction convs) on the tensor-core path: im2col + GEMM"""
+        return self.use_tc and self.tdtype == torch.bfloat16 and L["stride"] > 1 and x.dtype == torch.bfloat16
+
+    def _im2col(self, L, x, Ho, Wo):
+        col = self._empty(x.shape[0], Ho, Wo, L["taps"] * L["cin_p"])
+        ops.im2col(x, col, L["cin_p"], L["k"], L["k"], L["stride"], L["pad"])
+        return col
+
     def conv(self, x, name, y, bias=None, act=0, accumulate=0, out_nchw=0):
         L = self.L[name]
         w = self.wpack(name, 0)
+        if self._gemm_route(L, x) and not out_nchw:
+            col = self._im2col(L, x, y.shape[1], y.shape[2])
+            d = ops.make_desc(col, y, col.shape[-1], L["cout"], 1, 1, 1, 0, 0, act, accumulate, 0)
+            ops.conv_fwd(d, col, w, None if bias is None else self.P[bias].detach(), y, use_tc=True)
+            return
         d = ops.make_desc(x, y, L["cin_p"], L["cout"], L["k"], L["k"], L["stride"], L["pad"], 0, act, accumulate,
                           out_nchw)
         b = None if bias is None else self.P[bias].detach()
@@ -213,6 +229,14 @@ class Engine:
 
     def conv_dgrad(self, dy, name, dx, accumulate):
         L = self.L[name]
+        if self._gemm_route(L, dy):
+            w = self.wpack(name, 2)
+            K = L["taps"] * L["cin_p"]
+            dcol = self._empty(dy.shape[0], dy.shape[1], dy.shape[2], K)
+            d = ops.make_desc(dy, dcol, L["cout_p"], K, 1, 1, 1, 0)
+            ops.conv_fwd(d, dy, w, None, dcol, use_tc=True)
+            ops.col2im(dcol, dx, L["cin_p"], L["k"], L["k"], L["stride"], L["pad"], accumulate)
+            return
         w = self.wpack(name, 1)
         d = ops.make_desc(dy, dx, L["cout_p"], L["cin_p"], L["k"], L["k"], L["stride"], L["pad"], 1, 0,
                           int(accumulate), 0)
@@ -226,11 +250,16 @@ class Engine:
         direct = L["taps"] == 1 and L["cmap"] is None and L["cin_p"] == L["cin"]
         g = self.pg[name]
         dwp = g.view(L["cout"], L["cin"]) if direct else self.bwd_arena.take(L["cout"], L["taps"] * L["cin_p"])
-        d = ops.make_desc(x, dy, L["cin_p"], L["cout"], L["k"], L["k"], L["stride"], L["pad"], 0, 0, 0, 0)
-        ev = self._timed("wgrad", name)
-        ops.conv_wgrad(d, x, dy, dwp, use_tc=self.use_tc_wgrad and self._tc_ok(L, x, dy))
-        if ev is not None:
-            ev.record()
+        if self._gemm_route(L, x) and self.use_tc_wgrad:
+            col = self._im2col(L, x, dy.shape[1], dy.shape[2])      # recomputed: cheaper than keeping it alive
+            d = ops.make_desc(col, dy, col.shape[-1], L["cout"], 1, 1, 1, 0)
+            ops.conv_wgrad(d, col, dy, dwp, use_tc=True)
+        else:
+            d = ops.make_desc(x, dy, L["cin_p"], L["cout"], L["k"], L["k"], L["stride"], L["pad"], 0, 0, 0, 0)
+            ev = self._timed("wgrad", name)
+            ops.conv_wgrad(d, x, dy, dwp, use_tc=self.use_tc_wgrad and self._tc_ok(L, x, dy))
+            if ev is not None:
+                ev.record()
         if not direct:
             ops.weight_unpack_grad(dwp, g, self._cmap(name), L["cout"], L["cin"], L["taps"], L["cin_p"], False)
         if bias is not None:

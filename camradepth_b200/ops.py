@@ -108,6 +108,22 @@ def weight_unpack_grad(dwp, grad, cmap, Cout, Cin, taps, Cin_p, accumulate):
     K.crd_weight_unpack_grad(P(dwp), P(grad), P(cmap), Cout, Cin, taps, Cin_p, int(accumulate), stream())
 
 
+def im2col(x, col, Cin, KH, KW, stride, pad):
+    """x NHWC view (B,H,W,>=Cin) -> col (B,Ho,Wo,KH*KW*Cin) contiguous"""
+    B, H, W, _ = x.shape
+    _, Ho, Wo, _ = col.shape
+    assert col.is_contiguous() and col.shape[-1] == KH * KW * Cin
+    K.crd_im2col(P(x), P(col), dcode(x), B, H, W, Cin, _ld(x), Ho, Wo, KH, KW, stride, pad, stream())
+
+
+def col2im(dcol, dx, Cin, KH, KW, stride, pad, accumulate):
+    B, H, W, _ = dx.shape
+    _, Ho, Wo, _ = dcol.shape
+    assert dcol.is_contiguous()
+    K.crd_col2im(P(dcol), P(dx), dcode(dx), int(accumulate), B, H, W, Cin, _ld(dx), Ho, Wo, KH, KW, stride, pad,
+                 stream())
+
+
 def col_sum(dy, db, N):
     """db[:N] += column sums of the (M, ld) matrix behind the NHWC view dy."""
     M = dy.numel() // dy.shape[-1]

@@ -87,6 +87,7 @@ class diffGradNorm(Optimizer):
             if not params[0].is_cuda:
                 raise RuntimeError("camradepth_b200.diffGradNorm runs on CUDA devices only (no CPU fallback)")
             by_step = {}
+            capturing = torch.cuda.is_current_stream_capturing()
             for p in params:
                 if p.grad.is_sparse:
                     raise RuntimeError('diffGradNorm does not support sparse gradients')
@@ -98,7 +99,8 @@ class diffGradNorm(Optimizer):
                     st['previous_grad'] = torch.zeros_like(p.data)
                     st['exp_grad_norm'] = torch.zeros((), dtype=torch.float32, device=dev)
                     st['_slot'] = None
-                st['step'] += 1
+                if not capturing:          # a capture records the device work only; advance_for_replay() counts steps
+                    st['step'] += 1
                 by_step.setdefault(st['step'], []).append(p)
             beta1, beta2 = group['betas']
             for step_no, plist in by_step.items():

@@ -86,9 +86,17 @@ CRD_API int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const void*
 /* weight repacking between the reference's parameter layout and the kernels' K-major layout.
  * mode 0 (fwd):   dst[co][tap][map[ci]] = w[co][ci][tap]            dst is [Cout][KH*KW][Cin_p]
  * mode 1 (dgrad): dst[map[ci]][tap][co] = w[co][ci][tap]            dst is [Cin_p][KH*KW][Cout_p]
+ * mode 2 (dgrad of an im2col GEMM): dst[tap][map[ci]][co] = w[co][ci][tap]   dst is [KH*KW*Cin_p][Cout_p]
  * map == NULL is the identity; dst must be zero-filled by the caller where unmapped. */
 CRD_API int crd_weight_pack(const float* w, void* dst, int dst_dtype, const int* map, int Cout, int Cin, int taps,
                     int Cin_p, int Cout_p, int mode, crd_stream_t stream);
+/* Strided convolutions (patch embeddings k7s4/k3s2, spatial-reduction convs k=s; simplified_attention.py:68,
+ * 158-160) run as GEMMs on the tensor-core path: gather the patches once, multiply, scatter the data gradient.
+ * col is [B*Ho*Wo][KH*KW*Cin]; col2im is the gather-form adjoint. */
+CRD_API int crd_im2col(const void* x, void* col, int dtype, int B, int H, int W, int Cin, int ldx, int Ho, int Wo,
+               int KH, int KW, int stride, int pad, crd_stream_t stream);
+CRD_API int crd_col2im(const void* dcol, void* dx, int dtype, int accumulate, int B, int H, int W, int Cin, int lddx,
+               int Ho, int Wo, int KH, int KW, int stride, int pad, crd_stream_t stream);
 /* grad[co][ci][tap] (+)= dwp[co][tap][map[ci]] */
 CRD_API int crd_weight_unpack_grad(const float* dwp, float* grad, const int* map, int Cout, int Cin, int taps,
                            int Cin_p, int accumulate, crd_stream_t stream);

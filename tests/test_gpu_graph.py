@@ -36,9 +36,9 @@ def test_graphed_train_step_matches_eager():
     l_eager = [float(step1(b)) for _ in range(3)]
     for _ in range(3):
         step2(b)
-    g = GraphedTrainStep(step2, b, warmup=0)       # capture performs the 4th step
-    l_graph = [float(g.loss)]
-    for _ in range(2):
+    g = GraphedTrainStep(step2, b, warmup=0)       # capture records the step; it executes only on replay
+    l_graph = []
+    for _ in range(3):
         o2.advance_for_replay()
         l_graph.append(float(g(b)))
     torch.cuda.synchronize()

@@ -418,3 +418,27 @@ def test_diffgradnorm_matches_oracle():
         assert rel(p.detach().cpu(), r) < 1e-6
     for p, st in zip(ps, states):
         assert abs(float(opt.state[p]["exp_grad_norm"]) - float(st["exp_grad_norm"])) < 1e-4 * float(st["exp_grad_norm"])
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("case", [(2, 8, 32, 64, 7, 4, 3), (2, 64, 16, 24, 3, 2, 1), (2, 64, 16, 32, 8, 8, 0), (1, 160, 12, 26, 2, 2, 0)])
+def test_im2col_col2im(case, dtype):
+    """im2col is a pure gather; col2im must be its exact adjoint (<col2im(g), x> == <g, im2col(x)>)."""
+    from camradepth_b200 import ops
+    B, C, H, W, k, stride, pad = case
+    d = dev()
+    torch.manual_seed(9)
+    x = torch.randn(B, C, H, W, device=d)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    xb = nhwc(x, dtype)
+    col = torch.empty(B, Ho, Wo, k * k * C, dtype=dtype, device=d)
+    ops.im2col(xb, col, C, k, k, stride, pad)
+    ref = F.unfold(rnd(x, dtype), k, padding=pad, stride=stride)            # (B, C*k*k, L) with (c, kh, kw) order
+    ref = ref.view(B, C, k * k, Ho, Wo).permute(0, 3, 4, 2, 1).reshape(B, Ho, Wo, k * k * C)
+    assert torch.equal(col.float(), ref)
+    g = torch.randn(B, Ho, Wo, k * k * C, device=d).to(dtype)
+    dx = torch.ones(B, H, W, C, dtype=dtype, device=d)
+    ops.col2im(g, dx, C, k, k, stride, pad, True)
+    gr = g.float().view(B, Ho * Wo, k * k, C).permute(0, 3, 2, 1).reshape(B, C * k * k, Ho * Wo)
+    fold = F.fold(gr, (H, W), k, padding=pad, stride=stride)
+    assert rel(nchw(dx) - 1, fold) < (1e-5 if dtype == torch.float32 else 2e-2)
