@@ -32,8 +32,8 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const T* __restrict__ x
   }
   const T* xb = x + (long long)b * N * C + c;
   T* yb = y + (long long)b * N * C + c;
-  for (long long p = p0 + ry; p < p1; p += rows) {
-    const int hh = (int)(p / W), ww = (int)(p - (long long)hh * W);
+  for (int p = (int)p0 + ry; p < (int)p1; p += rows) {
+    const int hh = p / W, ww = p - hh * W;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[j] = bs[j];
@@ -46,12 +46,12 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const T* __restrict__ x
         const int w2 = ww + dw;
         if (w2 < 0 || w2 >= W) continue;
         float v[8];
-        load8(xb + ((long long)h2 * W + w2) * C, v);
+        load8(xb + (size_t)(h2 * W + w2) * C, v);
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[j] = fmaf(wt[(dh + 1) * 3 + (dw + 1)][j], fmaf(a[j], v[j], sh[j]), acc[j]);
       }
     }
-    store8(yb + p * C, acc);
+    store8(yb + (size_t)p * C, acc);
   }
 }
 
@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(256) dwconv_bwd_input_kernel(const T* __restri
     for (int t = 0; t < 9; t++) wt[t][j] = w[(c + j) * 9 + t];
   const T* gb = dy + (long long)b * N * C + c;
   T* ob = dxn + (long long)b * N * C + c;
-  for (long long p = p0 + ry; p < p1; p += rows) {
-    const int hh = (int)(p / W), ww = (int)(p - (long long)hh * W);
+  for (int p = (int)p0 + ry; p < (int)p1; p += rows) {
+    const int hh = p / W, ww = p - hh * W;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[j] = 0.f;
@@ -85,12 +85,12 @@ __global__ void __launch_bounds__(256) dwconv_bwd_input_kernel(const T* __restri
         const int w2 = ww - dw;
         if (w2 < 0 || w2 >= W) continue;
         float g[8];
-        load8(gb + ((long long)h2 * W + w2) * C, g);
+        load8(gb + (size_t)(h2 * W + w2) * C, g);
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[j] = fmaf(wt[(dh + 1) * 3 + (dw + 1)][j], g[j], acc[j]);
       }
     }
-    store8(ob + p * C, acc);
+    store8(ob + (size_t)p * C, acc);
   }
 }
 

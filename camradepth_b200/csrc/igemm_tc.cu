@@ -20,11 +20,9 @@ namespace {
 
 constexpr int TC_BM = 128;          // pixels per tile
 constexpr int TC_BK = 64;           // channels per k-chunk (128 bytes of bf16 = one swizzle row)
-constexpr int TC_STAGES = 3;
+constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
-constexpr int TC_B_BYTES = 128 * TC_BK * 2;
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_SMEM_BUDGET = 108 * 1024;      // per CTA, so that two CTAs fit one SM (epilogue of one overlaps MMAs of the other)
 constexpr int TC_THREADS = 192;
 
 struct TcParams {
@@ -37,7 +35,9 @@ struct TcParams {
   int kchunks;              // ceil(Cin / 64)
   int Cin;                  // K stride between taps in the packed weights
   int Cout;
-  int bn;                   // UMMA N of this launch (multiple of 16, <= 128)
+  int bn;                   // UMMA N = channels per N tile (multiple of 16, <= 256)
+  int nstages, stage_bytes; // smem ring geometry: stage = A (16 KB) + B (bn * 128 B)
+  int tmem_cols;            // 128 or 256
   int ldy, out_f32, act, accumulate;
 };
 
@@ -116,14 +116,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const TcParams p, const float* __restrict__ bias, void* __restrict__ yv) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024-B alignment
+  const int TC_STAGES = p.nstages, TC_STAGE_BYTES = p.stage_bytes;
   const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;
-  // barrier layout: full[STAGES], empty[STAGES], tmem_full, then the TMEM base address word
-  const uint32_t bar_full = bars, bar_empty = bars + 8 * TC_STAGES, bar_tmem = bars + 16 * TC_STAGES;
+  // barrier layout: full[MAX], empty[MAX], tmem_full, then the TMEM base address word
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * TC_MAX_STAGES, bar_tmem = bars + 16 * TC_MAX_STAGES;
   const uint32_t tmem_slot = bar_tmem + 8;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * 128;
+  const int n0 = blockIdx.y * p.bn;
   // tile coordinates
   int b = 0, oh0 = 0, ow0 = 0;
   long long m0 = 0;
@@ -145,8 +146,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
   }
-  if (warp == 1) {   // TMEM: 128 fp32 columns x 128 lanes
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128));
+  if (warp == 1) {   // TMEM: bn fp32 columns x 128 lanes (allocation granularity: power of two)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -258,7 +259,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
   }
 }
 
@@ -307,7 +308,8 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
   if (P == 0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TC_SMEM_BUDGET + 2048);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -340,25 +342,22 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
   const int Ktot = d->KH * d->KW * d->Cin;
   cudaStream_t s = (cudaStream_t)stream;
   const int gx = p.flat ? crd_div_up(P, TC_BM) : p.tiles_w * p.tiles_h * d->B;
-  // N is covered in tiles of 128; a ragged last tile runs as its own launch with a smaller UMMA N
-  const int nfull = d->Cout / 128, rem = d->Cout - nfull * 128;
-  for (int part = 0; part < 2; part++) {
-    const int ntiles = part == 0 ? nfull : (rem ? 1 : 0);
-    if (!ntiles) continue;
-    const int nbase = part == 0 ? 0 : nfull * 128;
-    p.bn = part == 0 ? 128 : (rem + 15) / 16 * 16;
-    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)(d->Cout - nbase)};
-    cuuint64_t str[1] = {(cuuint64_t)Ktot * 2};
-    cuuint32_t box[2] = {TC_BK, (cuuint32_t)p.bn};
-    rc = make_map(&map_b, (const bf16*)w + (long long)nbase * Ktot, 2, dims, str, box);
-    if (rc) return rc;
-    TcParams q = p;
-    q.Cout = d->Cout - nbase;
-    const float* bp = bias ? bias + nbase : nullptr;
-    void* yp = d->out_dtype == CRD_F32 ? (void*)((float*)y + nbase) : (void*)((bf16*)y + nbase);
-    conv_tc_kernel<<<dim3(gx, ntiles), TC_THREADS, TC_SMEM, s>>>(map_a, map_b, q, bp, yp);
-    CRD_LAUNCH_CHECK();
-  }
+  // N tiles of equal width <= 256 (one pass over A per tile; rows past Cout are zero-filled by TMA)
+  const int ntile = (d->Cout + 255) / 256;
+  p.bn = ((d->Cout + ntile - 1) / ntile + 15) / 16 * 16;
+  p.tmem_cols = p.bn <= 128 ? 128 : 256;
+  p.stage_bytes = TC_A_BYTES + p.bn * TC_BK * 2;
+  p.nstages = TC_SMEM_BUDGET / p.stage_bytes;
+  if (p.nstages > TC_MAX_STAGES) p.nstages = TC_MAX_STAGES;
+  if (p.nstages < 2) p.nstages = 2;
+  const int smem = p.nstages * p.stage_bytes + 1024 + 256;
+  cuuint64_t dimsb[2] = {(cuuint64_t)Ktot, (cuuint64_t)d->Cout};
+  cuuint64_t strb[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t boxb[2] = {TC_BK, (cuuint32_t)p.bn};
+  rc = make_map(&map_b, w, 2, dimsb, strb, boxb);
+  if (rc) return rc;
+  conv_tc_kernel<<<dim3(gx, ntile), TC_THREADS, smem, s>>>(map_a, map_b, p, bias, y);
+  CRD_LAUNCH_CHECK();
   return 0;
 }
 
@@ -373,8 +372,9 @@ namespace {
 // the KW shifted copies of X as its N blocks (or up to three 64-channel chunks of a 1x1 contraction), so
 // dY is fetched once per KW taps.  The pixel range is split over blockIdx.x; partial sums meet in fp32
 // with red.global.add (split-K), the accumulator lives in TMEM for the whole pixel loop.
-constexpr int WG_STAGES = 2;
-constexpr int WG_BLK_BYTES = 128 * 64 * 2;                      // one [128 px][64 ch] box
+constexpr int WG_STAGES = 5;
+constexpr int WG_PIX = 64;                                      // pixels (GEMM-K) per pipeline stage
+constexpr int WG_BLK_BYTES = WG_PIX * 64 * 2;                   // one [64 px][64 ch] box
 constexpr int WG_STAGE_BYTES = 5 * WG_BLK_BYTES;                // 2 dY blocks + 3 X blocks
 constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
 
@@ -456,7 +456,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
           mbar_expect_tx(bar, tx);
           long long t = t_begin + it;
           if (p.flat) {
-            const int m0 = (int)(t * 128);
+            const int m0 = (int)(t * WG_PIX);
             for (int j = 0; j < mblocks; j++) tma_load_2d(sa + j * WG_BLK_BYTES, &map_dy, bar, co0 + 64 * j, m0);
             for (int j = 0; j < nblk; j++) tma_load_2d(sb + j * WG_BLK_BYTES, &map_x, bar, c0 + 64 * j, m0);
           } else {
@@ -481,7 +481,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = base + s * WG_STAGE_BYTES, sb = sa + 2 * WG_BLK_BYTES;
 #pragma unroll
-          for (int k = 0; k < 8; k++) {       // 16 pixels (two 8-row groups = 2048 B) per MMA
+          for (int k = 0; k < WG_PIX / 16; k++) {       // 16 pixels (two 8-row groups = 2048 B) per MMA
             const uint64_t ad = umma_desc_mnmajor_sw128(sa + k * 2048, WG_BLK_BYTES);
             const uint64_t bd = umma_desc_mnmajor_sw128(sb + k * 2048, WG_BLK_BYTES);
             umma_bf16_ss(tmem_base, ad, bd, idesc, (it | k) != 0);
@@ -545,16 +545,16 @@ extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const vo
   p.mblocks = d->Cout > 64 ? 2 : 1;
   p.Ktot = (long long)d->KH * d->KW * d->Cin;
   p.TW = d->W >= 16 ? 16 : (d->W >= 8 ? 8 : 4);
-  p.TH = 128 / p.TW;
+  p.TH = WG_PIX / p.TW;
   p.tiles_w = (d->W + p.TW - 1) / p.TW;
   p.tiles_h = (d->H + p.TH - 1) / p.TH;
-  p.total_tiles = p.flat ? (P + 127) / 128 : (long long)p.tiles_w * p.tiles_h * d->B;
+  p.total_tiles = p.flat ? (P + WG_PIX - 1) / WG_PIX : (long long)p.tiles_w * p.tiles_h * d->B;
   CUtensorMap map_dy, map_x;
   int rc;
   if (p.flat) {
     cuuint64_t dims[2] = {(cuuint64_t)d->Cout, (cuuint64_t)P};
     cuuint64_t str[1] = {(cuuint64_t)d->ldy * 2};
-    cuuint32_t box[2] = {64, 128};
+    cuuint32_t box[2] = {64, WG_PIX};
     rc = make_map(&map_dy, dy, 2, dims, str, box);
     if (rc) return rc;
     cuuint64_t dims2[2] = {(cuuint64_t)d->Cin, (cuuint64_t)P};
@@ -575,7 +575,7 @@ extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const vo
   const int gz = (d->Cout + 127) / 128;
   // split the pixel tiles so that ~2 waves of CTAs cover the 148 SMs; each split handles >= 4 tiles
   long long want = (148LL * 2 + (long long)gy * gz - 1) / ((long long)gy * gz);
-  long long maxs = (p.total_tiles + 3) / 4;
+  long long maxs = (p.total_tiles + 7) / 8;
   long long splits = want < 1 ? 1 : (want > maxs ? maxs : want);
   if (splits < 1) splits = 1;
   p.tiles_per_split = (p.total_tiles + splits - 1) / splits;
