@@ -18,6 +18,7 @@ __device__ __forceinline__ void chan_reduce2(F f, float* out /*[B][C][2]*/, int 
   float s0[8], s1[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) { s0[j] = 0.f; s1[j] = 0.f; }
+#pragma unroll 4
   for (long long p = p0 + ry; p < p1; p += rows) f(b, p, cv * 8, s0, s1);
   // reduce over rows through shared memory
   float* r0 = red;                       // [rows][cvec*8]

@@ -54,6 +54,27 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = r;
 }
 
+// raw 8-element loads (kept packed so several can be in flight before any is unpacked)
+struct f32x8 { float4 lo, hi; };
+__device__ __forceinline__ uint4 ldg16(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ f32x8 ldg16(const float* p) {
+  f32x8 r;
+  r.lo = *reinterpret_cast<const float4*>(p);
+  r.hi = *reinterpret_cast<const float4*>(p + 4);
+  return r;
+}
+__device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void unpack8(const f32x8& r, float (&v)[8]) {
+  v[0] = r.lo.x; v[1] = r.lo.y; v[2] = r.lo.z; v[3] = r.lo.w; v[4] = r.hi.x; v[5] = r.hi.y; v[6] = r.hi.z; v[7] = r.hi.w;
+}
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> { typedef uint4 type; };
+template <> struct Raw8<float> { typedef f32x8 type; };
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -96,14 +96,17 @@ __global__ void bicubic_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx,
     for (int j = 0; j < 8; j++) acc[j] = 0.f;
 #pragma unroll
     for (int ty = 0; ty < 8; ty++) {
-      if (wy[ty] == 0.f) continue;
-      const int oy = 2 * sy - 3 + ty;
+      const int oy = min(max(2 * sy - 3 + ty, 0), Ho - 1);        // weight is 0 wherever the clamp acts
+      typename Raw8<T>::type raw[8];
 #pragma unroll
       for (int tx = 0; tx < 8; tx++) {
-        if (wx[tx] == 0.f) continue;
-        const int ox = 2 * sx - 3 + tx;
+        const int ox = min(max(2 * sx - 3 + tx, 0), Wo - 1);
+        raw[tx] = ldg16(dy + (((long long)b * Ho + oy) * Wo + ox) * lddy + cv * 8);
+      }
+#pragma unroll
+      for (int tx = 0; tx < 8; tx++) {
         float g[8];
-        load8(dy + (((long long)b * Ho + oy) * Wo + ox) * lddy + cv * 8, g);
+        unpack8(raw[tx], g);
         const float wgt = wy[ty] * wx[tx];
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[j] = fmaf(wgt, g[j], acc[j]);
@@ -220,6 +223,7 @@ __global__ void conv_c1_bwd_weight_kernel(const float* __restrict__ dy, const T*
       }
     }
   }
+#pragma unroll
   for (int q = 0; q < 10; q++) {
 #pragma unroll
     for (int j = 0; j < 8; j++) red[(ry * cvec + cv) * 8 + j] = acc[q][j];

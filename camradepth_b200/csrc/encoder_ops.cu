@@ -37,19 +37,23 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const T* __restrict__ x
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[j] = bs[j];
+    // branch-free taps: clamped addresses are always loadable, out-of-image taps are masked (zero padding
+    // applies to the NORMALISED tensor), so the nine 16-byte loads issue back to back
+    typename Raw8<T>::type raw[9];
+    bool ok[9];
 #pragma unroll
-    for (int dh = -1; dh <= 1; dh++) {
-      const int h2 = hh + dh;
-      if (h2 < 0 || h2 >= H) continue;
+    for (int t = 0; t < 9; t++) {
+      const int h2 = hh + t / 3 - 1, w2 = ww + t % 3 - 1;
+      ok[t] = (h2 >= 0) & (h2 < H) & (w2 >= 0) & (w2 < W);
+      const int hc = min(max(h2, 0), H - 1), wc = min(max(w2, 0), W - 1);
+      raw[t] = ldg16(xb + (size_t)(hc * W + wc) * C);
+    }
 #pragma unroll
-      for (int dw = -1; dw <= 1; dw++) {
-        const int w2 = ww + dw;
-        if (w2 < 0 || w2 >= W) continue;
-        float v[8];
-        load8(xb + (size_t)(h2 * W + w2) * C, v);
+    for (int t = 0; t < 9; t++) {
+      float v[8];
+      unpack8(raw[t], v);
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[j] = fmaf(wt[(dh + 1) * 3 + (dw + 1)][j], fmaf(a[j], v[j], sh[j]), acc[j]);
-      }
+      for (int j = 0; j < 8; j++) acc[j] = fmaf(wt[t][j], ok[t] ? fmaf(a[j], v[j], sh[j]) : 0.f, acc[j]);
     }
     store8(yb + (size_t)p * C, acc);
   }
@@ -76,19 +80,21 @@ __global__ void __launch_bounds__(256) dwconv_bwd_input_kernel(const T* __restri
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[j] = 0.f;
+    typename Raw8<T>::type raw[9];
+    bool ok[9];
 #pragma unroll
-    for (int dh = -1; dh <= 1; dh++) {
-      const int h2 = hh - dh;                 // output pixel that read this input with tap (dh,dw)
-      if (h2 < 0 || h2 >= H) continue;
+    for (int t = 0; t < 9; t++) {
+      const int h2 = hh - (t / 3 - 1), w2 = ww - (t % 3 - 1);   // output pixel that read this input with tap t
+      ok[t] = (h2 >= 0) & (h2 < H) & (w2 >= 0) & (w2 < W);
+      const int hc = min(max(h2, 0), H - 1), wc = min(max(w2, 0), W - 1);
+      raw[t] = ldg16(gb + (size_t)(hc * W + wc) * C);
+    }
 #pragma unroll
-      for (int dw = -1; dw <= 1; dw++) {
-        const int w2 = ww - dw;
-        if (w2 < 0 || w2 >= W) continue;
-        float g[8];
-        load8(gb + (size_t)(h2 * W + w2) * C, g);
+    for (int t = 0; t < 9; t++) {
+      float g[8];
+      unpack8(raw[t], g);
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[j] = fmaf(wt[(dh + 1) * 3 + (dw + 1)][j], g[j], acc[j]);
-      }
+      for (int j = 0; j < 8; j++) acc[j] = fmaf(wt[t][j], ok[t] ? g[j] : 0.f, acc[j]);
     }
     store8(ob + (size_t)p * C, acc);
   }
@@ -123,22 +129,24 @@ __global__ void dwconv_bwd_weight_kernel(const T* __restrict__ dy, const T* __re
     load8(dy + ((long long)b * N + p) * C + c, g);
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[9][j] += g[j];
+    typename Raw8<T>::type raw[9];
+    bool ok[9];
 #pragma unroll
-    for (int dh = -1; dh <= 1; dh++) {
-      const int h2 = hh + dh;
-      if (h2 < 0 || h2 >= H) continue;
+    for (int t = 0; t < 9; t++) {
+      const int h2 = hh + t / 3 - 1, w2 = ww + t % 3 - 1;
+      ok[t] = (h2 >= 0) & (h2 < H) & (w2 >= 0) & (w2 < W);
+      const int hc = min(max(h2, 0), H - 1), wc = min(max(w2, 0), W - 1);
+      raw[t] = ldg16(x + (((long long)b * H + hc) * W + wc) * C + c);
+    }
 #pragma unroll
-      for (int dw_ = -1; dw_ <= 1; dw_++) {
-        const int w2 = ww + dw_;
-        if (w2 < 0 || w2 >= W) continue;
-        float v[8];
-        load8(x + (((long long)b * H + h2) * W + w2) * C + c, v);
-        const int tap = (dh + 1) * 3 + (dw_ + 1);
+    for (int t = 0; t < 9; t++) {
+      float v[8];
+      unpack8(raw[t], v);
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[tap][j] = fmaf(g[j], fmaf(a[j], v[j], sh[j]), acc[tap][j]);
-      }
+      for (int j = 0; j < 8; j++) acc[t][j] = fmaf(g[j], ok[t] ? fmaf(a[j], v[j], sh[j]) : 0.f, acc[t][j]);
     }
   }
+#pragma unroll
   for (int q = 0; q < 10; q++) {
 #pragma unroll
     for (int j = 0; j < 8; j++) red[(ry * cvec + cv) * 8 + j] = acc[q][j];

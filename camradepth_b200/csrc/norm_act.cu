@@ -91,13 +91,29 @@ __global__ void affine_act_kernel(const TI* __restrict__ x, TO* __restrict__ y, 
   }
   const TI* xb = x + (long long)b * N * ldx + c;
   TO* yb = y + (long long)b * N * ldy + c;
-#pragma unroll 2
-  for (long long p = p0 + ry; p < p1; p += rows) {
-    float v[8];
-    load8(xb + p * ldx, v);
+  // four independent 16-byte loads in flight per thread before any is consumed
+  for (long long p = p0 + ry; p < p1; p += 4LL * rows) {
+    typename Raw8<TI>::type raw[4];
 #pragma unroll
-    for (int j = 0; j < 8; j++) v[j] = act_fwd(fmaf(a[j], v[j], sh[j]), act) * ps[j];
-    store8(yb + p * ldy, v);
+    for (int u = 0; u < 4; u++) {
+      const long long q = p + (long long)u * rows;
+      raw[u] = ldg16(xb + (q < p1 ? q : p) * ldx);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long long q = p + (long long)u * rows;
+      if (q >= p1) break;
+      float v[8];
+      unpack8(raw[u], v);
+      if (act == CRD_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = gelu_f(fmaf(a[j], v[j], sh[j])) * ps[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = act_fwd(fmaf(a[j], v[j], sh[j]), act) * ps[j];
+      }
+      store8(yb + q * ldy, v);
+    }
   }
 }
 
@@ -200,20 +216,36 @@ __global__ void gnact_bwd_apply_kernel(const TD* __restrict__ dy, const TX* __re
   const TD* dyb = dy + (long long)b * N * lddy + c;
   const TX* xb = x + (long long)b * N * ldx + c;
   TO* dxb = dx + (long long)b * N * lddx + c;
-#pragma unroll 2
-  for (long long p = p0 + ry; p < p1; p += rows) {
-    float g[8], v[8], o[8];
-    load8(dyb + p * lddy, g);
-    load8(xb + p * ldx, v);
-    if (accumulate) load8(dxb + p * lddx, o);
+  for (long long p = p0 + ry; p < p1; p += 2LL * rows) {
+    typename Raw8<TD>::type rg[2];
+    typename Raw8<TX>::type rx[2];
+    typename Raw8<TO>::type ro[2];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      float dz = (g[j] + ad[j]) * ps[j];
-      if (act != CRD_ACT_NONE) dz *= act_bwd(fmaf(a[j], v[j], sh[j]), act);
-      const float r = fmaf(cA[j], dz, fmaf(cB[j], v[j], cC[j]));
-      o[j] = accumulate ? o[j] + r : r;
+    for (int u = 0; u < 2; u++) {
+      const long long q = p + (long long)u * rows;
+      const long long qq = q < p1 ? q : p;
+      rg[u] = ldg16(dyb + qq * lddy);
+      rx[u] = ldg16(xb + qq * ldx);
+      if (accumulate) ro[u] = ldg16(dxb + qq * lddx);
     }
-    store8(dxb + p * lddx, o);
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const long long q = p + (long long)u * rows;
+      if (q >= p1) break;
+      float g[8], v[8], o[8];
+      unpack8(rg[u], g);
+      unpack8(rx[u], v);
+      if (accumulate) unpack8(ro[u], o);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        float dz = (g[j] + ad[j]) * ps[j];
+        if (act == CRD_ACT_GELU) dz *= gelu_grad_f(fmaf(a[j], v[j], sh[j]));
+        else if (act != CRD_ACT_NONE) dz *= act_bwd(fmaf(a[j], v[j], sh[j]), act);
+        const float r = fmaf(cA[j], dz, fmaf(cB[j], v[j], cC[j]));
+        o[j] = accumulate ? o[j] + r : r;
+      }
+      store8(dxb + q * lddx, o);
+    }
   }
 }
 
