@@ -120,8 +120,8 @@ __global__ void affine_act_kernel(const TI* __restrict__ x, TO* __restrict__ y, 
 template <typename TD, typename TX>
 __global__ void gnact_bwd_reduce_kernel(const TD* __restrict__ dy, const TX* __restrict__ x,
                                         const float* __restrict__ ab, const float* __restrict__ post,
-                                        const float* __restrict__ addbc, int act, float* pq, int B, long long N,
-                                        int C, int lddy, int ldx, long long ppb) {
+                                        const float* __restrict__ addbc, int act, float* pq, TD* dz_out, int B,
+                                        long long N, int C, int lddy, int ldx, long long ppb) {
   const int c0 = threadIdx.x * 8, b0 = blockIdx.y;
   float a[8], sh[8], ps[8], ad[8];
 #pragma unroll
@@ -139,10 +139,14 @@ __global__ void gnact_bwd_reduce_kernel(const TD* __restrict__ dy, const TX* __r
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       float dz = (g[j] + ad[j]) * ps[j];
-      if (act != CRD_ACT_NONE) dz *= act_bwd(fmaf(a[j], v[j], sh[j]), act);
+      if (act == CRD_ACT_GELU) dz *= gelu_grad_f(fmaf(a[j], v[j], sh[j]));
+      else if (act != CRD_ACT_NONE) dz *= act_bwd(fmaf(a[j], v[j], sh[j]), act);
+      g[j] = dz;
       s0[j] += dz;
       s1[j] = fmaf(dz, v[j], s1[j]);
     }
+    // optionally materialise dz (may alias dy): the apply pass then skips the activation derivative
+    if (dz_out) store8(dz_out + pix * lddy + c, g);
   }, pq, B, N, C, ppb);
 }
 
@@ -287,14 +291,14 @@ extern "C" int crd_affine_act(const void* x, int in_dtype, void* y, int out_dtyp
 }
 
 extern "C" int crd_gnact_bwd_reduce(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* ab,
-                                    const float* post, const float* addbc, int act, float* pq, int B,
-                                    long long N, int C, int lddy, int ldx, crd_stream_t stream) {
+                                    const float* post, const float* addbc, int act, float* pq, void* dz_out,
+                                    int B, long long N, int C, int lddy, int ldx, crd_stream_t stream) {
   CRD_REQUIRE(C % 8 == 0 && C / 8 <= 256 && lddy % 8 == 0 && ldx % 8 == 0);
   if (B == 0 || N == 0) return 0;
   ReduceLaunch r = plan_reduce(B, N, C);
   cudaStream_t s = (cudaStream_t)stream;
   CRD_DISPATCH_1(dy_dtype, TD, CRD_DISPATCH_1(x_dtype, TX, gnact_bwd_reduce_kernel<TD, TX><<<r.grid, r.block, r.smem, s>>>(
-                                   (const TD*)dy, (const TX*)x, ab, post, addbc, act, pq, B, N, C, lddy, ldx, r.ppb)));
+                                   (const TD*)dy, (const TX*)x, ab, post, addbc, act, pq, (TD*)dz_out, B, N, C, lddy, ldx, r.ppb)));
   CRD_LAUNCH_CHECK();
   return 0;
 }

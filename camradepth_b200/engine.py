@@ -279,11 +279,17 @@ class Engine:
     def gn_bwd(self, dy, x, ab, mr, prefix, G, act, post, addbc, dx, accumulate):
         B, N, C = ops._bnc(x)
         pq = self.bwd_arena.take(B, C, 2)
-        ops.gnact_bwd_reduce(dy, x, ab, post, addbc, act, pq)
+        # with an activation, dz = dy * post * act'(.) is written back over dy by the reduce pass (every such dy is
+        # consumed only here), so the derivative is evaluated once and the apply pass is a pure stream
+        inplace = act != ops.ACT_NONE
+        ops.gnact_bwd_reduce(dy, x, ab, post, addbc, act, pq, dy if inplace else None)
         coef = self._empty(B, C, 3, dtype=torch.float32)
         ops.gn_bwd_finalize(pq, mr, self.P[prefix + ".weight"].detach(), coef, self.pg[prefix + ".weight"],
                             self.pg[prefix + ".bias"], B, C, G, N)
-        ops.gnact_bwd_apply(dy, x, ab, post, addbc, act, coef, dx, accumulate)
+        if inplace:
+            ops.gnact_bwd_apply(dy, x, ab, None, None, ops.ACT_NONE, coef, dx, accumulate)
+        else:
+            ops.gnact_bwd_apply(dy, x, ab, post, addbc, act, coef, dx, accumulate)
 
     # ------------------------------------------------------------------ masks
     def make_masks(self, B):

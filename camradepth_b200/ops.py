@@ -152,10 +152,12 @@ def affine_act(x, y, ab, post, act):
     K.crd_affine_act(P(x), dcode(x), P(y), dcode(y), P(ab), P(post), act, B, N, C, _ld(x), _ld(y), stream())
 
 
-def gnact_bwd_reduce(dy, x, ab, post, addbc, act, pq):
+def gnact_bwd_reduce(dy, x, ab, post, addbc, act, pq, dz_out=None):
     B, N, C = _bnc(x)
-    K.crd_gnact_bwd_reduce(P(dy), dcode(dy), P(x), dcode(x), P(ab), P(post), P(addbc), act, P(pq), B, N, C,
-                           _ld(dy), _ld(x), stream())
+    if dz_out is not None:
+        assert dz_out.dtype == dy.dtype and _ld(dz_out) == _ld(dy)
+    K.crd_gnact_bwd_reduce(P(dy), dcode(dy), P(x), dcode(x), P(ab), P(post), P(addbc), act, P(pq), P(dz_out), B, N,
+                           C, _ld(dy), _ld(x), stream())
 
 
 def gn_bwd_finalize(pq, mean_rstd, gamma, coef, dgamma, dbeta, B, C, G, N):

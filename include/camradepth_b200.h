@@ -114,10 +114,12 @@ CRD_API int crd_gn_finalize(const float* sums, const float* gamma, const float* 
 /* y = act(a*x+b) * post[b][c] */
 CRD_API int crd_affine_act(const void* x, int in_dtype, void* y, int out_dtype, const float* ab, const float* post,
                    int act, int B, long long N, int C, int ldx, int ldy, crd_stream_t stream);
-/* backward: dz = (dy + addbc[b][c]) * post * act'(a*x+b);  pq[b][c] += (sum dz, sum dz*x) */
+/* backward: dz = (dy + addbc[b][c]) * post * act'(a*x+b);  pq[b][c] += (sum dz, sum dz*x).
+ * dz_out (optional, layout/dtype of dy, may alias dy) receives dz so that crd_gnact_bwd_apply can run with
+ * act = NONE, post = addbc = NULL on it (the activation derivative is evaluated once, not twice). */
 CRD_API int crd_gnact_bwd_reduce(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* ab,
-                         const float* post, const float* addbc, int act, float* pq, int B, long long N, int C,
-                         int lddy, int ldx, crd_stream_t stream);
+                         const float* post, const float* addbc, int act, float* pq, void* dz_out, int B,
+                         long long N, int C, int lddy, int ldx, crd_stream_t stream);
 /* coef[b][c][3] = (A, Bq, Cq) with dx = A*dz + Bq*x + Cq ; dgamma/dbeta[c] += ... */
 CRD_API int crd_gn_bwd_finalize(const float* pq, const float* mean_rstd, const float* gamma, float* coef,
                         float* dgamma, float* dbeta, int B, int C, int G, long long N, crd_stream_t stream);

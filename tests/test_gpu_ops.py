@@ -182,6 +182,14 @@ def test_groupnorm_protocol(shape, act, dtype):
     dx2 = torch.empty(B, H, W, C, dtype=dtype, device=d)
     ops.gnact_bwd_apply(dy, xb, ab, post, addbc, act, coef, dx2, False)
     assert rel(nchw(dx2), gx_ref) < max(t, TOL[dtype])
+    # variant used by the engine: the reduce pass materialises dz in place, the apply pass is a pure stream
+    dz = dy.clone()
+    pq2 = torch.zeros(B, C, 2, device=d)
+    ops.gnact_bwd_reduce(dz, xb, ab, post, addbc, act, pq2, dz)
+    assert rel(pq2, pq) < 1e-5
+    dx3 = torch.empty(B, H, W, C, dtype=dtype, device=d)
+    ops.gnact_bwd_apply(dz, xb, ab, None, None, ops.ACT_NONE, coef, dx3, False)
+    assert rel(nchw(dx3), gx_ref) < max(t, 2 * TOL[dtype])
 
 
 @pytest.mark.parametrize("dtype", DT)

@@ -25,6 +25,13 @@ TC_CASES = [
     (2, 64, 48, 104, 512, 1),     # fc1-like
     (2, 1024, 6, 13, 256, 1),     # fc2-like, long K
     (1, 256, 3, 5, 256, 1),
+    # H % 16 == 0: the halo-reuse kernel (two accumulators per CTA, 18-row activation boxes)
+    (2, 136, 32, 48, 96, 3),
+    (1, 232, 16, 32, 64, 3),      # dgrad output 232 -> two N tiles of 128
+    (2, 128, 16, 24, 21, 3),      # ragged N, partial tile in W
+    (1, 129, 32, 16, 128, 3),     # dgrad output 136 -> one N tile of 144 (accumulators 256 TMEM columns apart)
+    (1, 296, 16, 16, 128, 3),     # dgrad output 296 -> two N tiles of 160
+    (3, 64, 48, 104, 32, 3),
 ]
 
 

@@ -45,6 +45,7 @@ for (B, N, C, ld) in SHAPES:
     report("chan_stats " + tag, timeit(lambda: ops.chan_stats(x, sums)), e)
     report("affine_act gelu " + tag, timeit(lambda: ops.affine_act(x, big[..., :C], ab, post, ops.ACT_GELU)), 2 * e)
     report("gnact_bwd_reduce gelu " + tag, timeit(lambda: ops.gnact_bwd_reduce(dy, x, ab, post, None, ops.ACT_GELU, pq)), 2 * e)
+    report("gnact_bwd_reduce gelu + dz " + tag, timeit(lambda: ops.gnact_bwd_reduce(dy, x, ab, post, None, ops.ACT_GELU, pq, dy)), 3 * e)
     report("gnact_bwd_apply gelu " + tag, timeit(lambda: ops.gnact_bwd_apply(dy, x, ab, post, None, ops.ACT_GELU, coef, out, False)), 3 * e)
     report("gnact_bwd_apply none " + tag, timeit(lambda: ops.gnact_bwd_apply(dy, x, ab, None, None, ops.ACT_NONE, coef, out, False)), 3 * e)
     if C >= 512:
