@@ -471,7 +471,7 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
   cudaStream_t s = (cudaStream_t)stream;
   static int use_halo = -1;
   if (use_halo < 0) { const char* e = getenv("CAMRADEPTH_TC_HALO"); use_halo = (e && e[0] == '0') ? 0 : 1; }
-  if (use_halo && d->KH == 3 && d->H % 16 == 0 && d->W >= 16) {
+  if (use_halo && d->KH == 3 && d->H % 16 == 0 && d->W >= 16 && d->Cin >= 136 && d->Cout >= 64) {
     static bool halo_attr = false;
     if (!halo_attr) {
       cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -609,6 +609,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     if (warp == 0) {
       if (lane == 0) {
         const uint32_t tx = (uint32_t)(mblocks + nblk) * WG_BLK_BYTES;
+        // tile coordinates advance incrementally (no 64-bit divisions on the producer's critical path)
+        int tw = 0, th = 0, bb = 0, m0 = 0;
+        if (p.flat) {
+          m0 = (int)(t_begin * WG_PIX);
+        } else {
+          long long t = t_begin;
+          tw = (int)(t % p.tiles_w); t /= p.tiles_w;
+          th = (int)(t % p.tiles_h); t /= p.tiles_h;
+          bb = (int)t;
+        }
         for (int it = 0; it < ntiles; it++) {
           const int s = it % WG_STAGES;
           const uint32_t ph = (it / WG_STAGES) & 1;
@@ -616,19 +626,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
           const uint32_t sa = base + s * WG_STAGE_BYTES, sb = sa + 2 * WG_BLK_BYTES;
           const uint32_t bar = bar_full + 8 * s;
           mbar_expect_tx(bar, tx);
-          long long t = t_begin + it;
           if (p.flat) {
-            const int m0 = (int)(t * WG_PIX);
             for (int j = 0; j < mblocks; j++) tma_load_2d(sa + j * WG_BLK_BYTES, &map_dy, bar, co0 + 64 * j, m0);
             for (int j = 0; j < nblk; j++) tma_load_2d(sb + j * WG_BLK_BYTES, &map_x, bar, c0 + 64 * j, m0);
+            m0 += WG_PIX;
           } else {
-            const int tw = (int)(t % p.tiles_w); t /= p.tiles_w;
-            const int th = (int)(t % p.tiles_h); t /= p.tiles_h;
-            const int b = (int)t, oh0 = th * p.TH, ow0 = tw * p.TW;
+            const int oh0 = th * p.TH, ow0 = tw * p.TW;
             for (int j = 0; j < mblocks; j++)
-              tma_load_4d(sa + j * WG_BLK_BYTES, &map_dy, bar, co0 + 64 * j, ow0, oh0, b);
+              tma_load_4d(sa + j * WG_BLK_BYTES, &map_dy, bar, co0 + 64 * j, ow0, oh0, bb);
             for (int j = 0; j < nblk; j++)
-              tma_load_4d(sb + j * WG_BLK_BYTES, &map_x, bar, c0, ow0 + j - p.pad, oh0 + kh - p.pad, b);
+              tma_load_4d(sb + j * WG_BLK_BYTES, &map_x, bar, c0, ow0 + j - p.pad, oh0 + kh - p.pad, bb);
+            if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++bb; } }
           }
         }
       }
