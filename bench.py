@@ -154,6 +154,8 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--graph-multi", type=int, default=int(os.environ.get("CAMRADEPTH_GRAPH_MULTI", "0")),
+                    help="also capture the step (incl. the NCCL all-reduces) into a CUDA graph when N > 1")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
@@ -210,7 +212,7 @@ def main():
         torch.cuda.synchronize()
 
     from camradepth_b200.graphs import GraphedTrainStep
-    use_graph = (not a.no_graph) and world == 1
+    use_graph = (not a.no_graph) and (world == 1 or a.graph_multi == 1)
     for _ in range(a.warmup):
         step(devb)
     eng = model._engines[a.precision]

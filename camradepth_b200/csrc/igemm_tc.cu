@@ -534,11 +534,8 @@ namespace {
 // the KW shifted copies of X as its N blocks (or up to three 64-channel chunks of a 1x1 contraction), so
 // dY is fetched once per KW taps.  The pixel range is split over blockIdx.x; partial sums meet in fp32
 // with red.global.add (split-K), the accumulator lives in TMEM for the whole pixel loop.
-constexpr int WG_STAGES = 5;
-constexpr int WG_PIX = 64;                                      // pixels (GEMM-K) per pipeline stage
-constexpr int WG_BLK_BYTES = WG_PIX * 64 * 2;                   // one [64 px][64 ch] box
-constexpr int WG_STAGE_BYTES = 5 * WG_BLK_BYTES;                // 2 dY blocks + 3 X blocks
-constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+constexpr int WG_MAX_STAGES = 10;
+constexpr int WG_SMEM = 200 * 1024 + 1024 + 256;                // ring of WG_STAGES stages of 5 boxes [PIX px][64 ch]
 
 struct WgParams {
   int flat, TW, TH, tiles_w, tiles_h;
@@ -561,13 +558,17 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t saddr, uint
   return d;
 }
 
+template <int WG_PIX>          // pixels (GEMM-K) per pipeline stage: 32, 64 or 128
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                 const WgParams p, float* __restrict__ dw) {
+  constexpr int WG_BLK_BYTES = WG_PIX * 64 * 2;
+  constexpr int WG_STAGE_BYTES = 5 * WG_BLK_BYTES;                // 2 dY blocks + 3 X blocks
+  constexpr int WG_STAGES = (200 * 1024) / WG_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + WG_STAGES * WG_STAGE_BYTES;
-  const uint32_t bar_full = bars, bar_empty = bars + 8 * WG_STAGES, bar_tmem = bars + 16 * WG_STAGES;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * WG_MAX_STAGES, bar_tmem = bars + 16 * WG_MAX_STAGES;
   const uint32_t tmem_slot = bar_tmem + 8;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -701,11 +702,15 @@ extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const vo
   CRD_REQUIRE(d->KH == d->KW && 2 * d->pad == d->KH - 1 && d->KW <= 3);
   const long long P = (long long)d->B * d->H * d->W;
   if (P == 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+  static int WG_PIX = 0;
+  if (!WG_PIX) {
+    const char* e = getenv("CAMRADEPTH_WG_PIX");
+    WG_PIX = e ? atoi(e) : 64;
+    if (WG_PIX != 32 && WG_PIX != 64 && WG_PIX != 128) WG_PIX = 64;
+    cudaError_t e1 = cudaFuncSetAttribute(wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    cudaError_t e2 = cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    cudaError_t e3 = cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { WG_PIX = 0; return (int)(e1 ? e1 : (e2 ? e2 : e3)); }
   }
   WgParams p;
   p.flat = (d->KH == 1);
@@ -750,7 +755,11 @@ extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const vo
   if (splits < 1) splits = 1;
   p.tiles_per_split = (p.total_tiles + splits - 1) / splits;
   splits = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  wgrad_tc_kernel<<<dim3((unsigned)splits, gy, gz), TC_THREADS, WG_SMEM, (cudaStream_t)stream>>>(map_dy, map_x, p, dw);
+  const dim3 grid((unsigned)splits, gy, gz);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (WG_PIX == 32) wgrad_tc_kernel<32><<<grid, TC_THREADS, WG_SMEM, st>>>(map_dy, map_x, p, dw);
+  else if (WG_PIX == 64) wgrad_tc_kernel<64><<<grid, TC_THREADS, WG_SMEM, st>>>(map_dy, map_x, p, dw);
+  else wgrad_tc_kernel<128><<<grid, TC_THREADS, WG_SMEM, st>>>(map_dy, map_x, p, dw);
   CRD_LAUNCH_CHECK();
   return 0;
 }
