@@ -38,6 +38,27 @@ __device__ __forceinline__ void chan_reduce2(F f, float* out /*[B][C][2]*/, int 
   }
 }
 
+// Tail of every per-(b,c) reduction: rows -> shared memory -> one atomic per (block, channel, quantity).
+__device__ __forceinline__ void chan_reduce_finish(float (&s0)[8], float (&s1)[8], float* out, int b, int C) {
+  extern __shared__ float red[];
+  const int cv = threadIdx.x, ry = threadIdx.y, rows = blockDim.y, cvec = blockDim.x;
+  float* r0 = red;
+  float* r1 = red + (size_t)rows * cvec * 8;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    r0[(ry * cvec + cv) * 8 + j] = s0[j];
+    r1[(ry * cvec + cv) * 8 + j] = s1[j];
+  }
+  __syncthreads();
+  const int t = ry * cvec + cv, nt = rows * cvec;
+  for (int c = t; c < C; c += nt) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int r = 0; r < rows; r++) { a0 += r0[r * cvec * 8 + c]; a1 += r1[r * cvec * 8 + c]; }
+    atomicAdd(out + ((long long)b * C + c) * 2 + 0, a0);
+    atomicAdd(out + ((long long)b * C + c) * 2 + 1, a1);
+  }
+}
+
 struct ReduceLaunch { dim3 grid, block; size_t smem; long long ppb; };
 inline ReduceLaunch plan_reduce(int B, long long N, int C) {
   ReduceLaunch r;

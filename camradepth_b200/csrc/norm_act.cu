@@ -12,12 +12,31 @@ namespace {
 template <typename T>
 __global__ void chan_stats_kernel(const T* __restrict__ x, float* sums, int B, long long N, int C, int ld,
                                   long long ppb) {
-  chan_reduce2([&](int b, long long p, int c, float (&s0)[8], float (&s1)[8]) {
-    float v[8];
-    load8(x + ((long long)b * N + p) * ld + c, v);
+  const int c = threadIdx.x * 8, ry = threadIdx.y, rows = blockDim.y, b = blockIdx.y;
+  long long p0 = (long long)blockIdx.x * ppb, p1 = p0 + ppb;
+  if (p1 > N) p1 = N;
+  const T* xb = x + (long long)b * N * ld + c;
+  float s0[8], s1[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) { s0[j] += v[j]; s1[j] = fmaf(v[j], v[j], s1[j]); }
-  }, sums, B, N, C, ppb);
+  for (int j = 0; j < 8; j++) { s0[j] = 0.f; s1[j] = 0.f; }
+  constexpr int U = 8;                         // eight independent 16-byte loads in flight per thread
+  for (long long p = p0 + ry; p < p1; p += (long long)U * rows) {
+    typename Raw8<T>::type raw[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long q = p + (long long)u * rows;
+      raw[u] = ldg16(xb + (q < p1 ? q : p) * ld);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (p + (long long)u * rows >= p1) break;
+      float v[8];
+      unpack8(raw[u], v);
+#pragma unroll
+      for (int j = 0; j < 8; j++) { s0[j] += v[j]; s1[j] = fmaf(v[j], v[j], s1[j]); }
+    }
+  }
+  chan_reduce_finish(s0, s1, sums, b, C);
 }
 
 __global__ void gn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
@@ -122,32 +141,55 @@ __global__ void gnact_bwd_reduce_kernel(const TD* __restrict__ dy, const TX* __r
                                         const float* __restrict__ ab, const float* __restrict__ post,
                                         const float* __restrict__ addbc, int act, float* pq, TD* dz_out, int B,
                                         long long N, int C, int lddy, int ldx, long long ppb) {
-  const int c0 = threadIdx.x * 8, b0 = blockIdx.y;
+  const int c = threadIdx.x * 8, ry = threadIdx.y, rows = blockDim.y, b = blockIdx.y;
+  long long p0 = (long long)blockIdx.x * ppb, p1 = p0 + ppb;
+  if (p1 > N) p1 = N;
   float a[8], sh[8], ps[8], ad[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) {
-    a[j] = ab[((long long)b0 * C + c0 + j) * 2];
-    sh[j] = ab[((long long)b0 * C + c0 + j) * 2 + 1];
-    ps[j] = post ? post[(long long)b0 * C + c0 + j] : 1.f;
-    ad[j] = addbc ? addbc[(long long)b0 * C + c0 + j] : 0.f;
+    a[j] = ab[((long long)b * C + c + j) * 2];
+    sh[j] = ab[((long long)b * C + c + j) * 2 + 1];
+    ps[j] = post ? post[(long long)b * C + c + j] : 1.f;
+    ad[j] = addbc ? addbc[(long long)b * C + c + j] : 0.f;
   }
-  chan_reduce2([&](int b, long long p, int c, float (&s0)[8], float (&s1)[8]) {
-    float g[8], v[8];
-    const long long pix = (long long)b * N + p;
-    load8(dy + pix * lddy + c, g);
-    load8(x + pix * ldx + c, v);
+  const TD* dyb = dy + (long long)b * N * lddy + c;
+  const TX* xb = x + (long long)b * N * ldx + c;
+  TD* dzb = dz_out ? dz_out + (long long)b * N * lddy + c : nullptr;
+  float s0[8], s1[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      float dz = (g[j] + ad[j]) * ps[j];
-      if (act == CRD_ACT_GELU) dz *= gelu_grad_f(fmaf(a[j], v[j], sh[j]));
-      else if (act != CRD_ACT_NONE) dz *= act_bwd(fmaf(a[j], v[j], sh[j]), act);
-      g[j] = dz;
-      s0[j] += dz;
-      s1[j] = fmaf(dz, v[j], s1[j]);
+  for (int j = 0; j < 8; j++) { s0[j] = 0.f; s1[j] = 0.f; }
+  constexpr int U = 4;                         // four (dy, x) pairs in flight per thread
+  for (long long p = p0 + ry; p < p1; p += (long long)U * rows) {
+    typename Raw8<TD>::type rg[U];
+    typename Raw8<TX>::type rx[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long q = p + (long long)u * rows;
+      const long long qq = q < p1 ? q : p;
+      rg[u] = ldg16(dyb + qq * lddy);
+      rx[u] = ldg16(xb + qq * ldx);
     }
-    // optionally materialise dz (may alias dy): the apply pass then skips the activation derivative
-    if (dz_out) store8(dz_out + pix * lddy + c, g);
-  }, pq, B, N, C, ppb);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long q = p + (long long)u * rows;
+      if (q >= p1) break;
+      float g[8], v[8];
+      unpack8(rg[u], g);
+      unpack8(rx[u], v);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        float dz = (g[j] + ad[j]) * ps[j];
+        if (act == CRD_ACT_GELU) dz *= gelu_grad_f(fmaf(a[j], v[j], sh[j]));
+        else if (act != CRD_ACT_NONE) dz *= act_bwd(fmaf(a[j], v[j], sh[j]), act);
+        g[j] = dz;
+        s0[j] += dz;
+        s1[j] = fmaf(dz, v[j], s1[j]);
+      }
+      // optionally materialise dz (may alias dy): the apply pass then skips the activation derivative
+      if (dzb) store8(dzb + q * lddy, g);
+    }
+  }
+  chan_reduce_finish(s0, s1, pq, b, C);
 }
 
 __global__ void gn_bwd_finalize_kernel(const float* __restrict__ pq, const float* __restrict__ mean_rstd,
@@ -220,12 +262,13 @@ __global__ void gnact_bwd_apply_kernel(const TD* __restrict__ dy, const TX* __re
   const TD* dyb = dy + (long long)b * N * lddy + c;
   const TX* xb = x + (long long)b * N * ldx + c;
   TO* dxb = dx + (long long)b * N * lddx + c;
-  for (long long p = p0 + ry; p < p1; p += 2LL * rows) {
-    typename Raw8<TD>::type rg[2];
-    typename Raw8<TX>::type rx[2];
-    typename Raw8<TO>::type ro[2];
+  constexpr int U = 4;
+  for (long long p = p0 + ry; p < p1; p += (long long)U * rows) {
+    typename Raw8<TD>::type rg[U];
+    typename Raw8<TX>::type rx[U];
+    typename Raw8<TO>::type ro[U];
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
+    for (int u = 0; u < U; u++) {
       const long long q = p + (long long)u * rows;
       const long long qq = q < p1 ? q : p;
       rg[u] = ldg16(dyb + qq * lddy);
@@ -233,7 +276,7 @@ __global__ void gnact_bwd_apply_kernel(const TD* __restrict__ dy, const TX* __re
       if (accumulate) ro[u] = ldg16(dxb + qq * lddx);
     }
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
+    for (int u = 0; u < U; u++) {
       const long long q = p + (long long)u * rows;
       if (q >= p1) break;
       float g[8], v[8], o[8];
