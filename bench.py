@@ -154,8 +154,6 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--graph-multi", type=int, default=int(os.environ.get("CAMRADEPTH_GRAPH_MULTI", "0")),
-                    help="also capture the step (incl. the NCCL all-reduces) into a CUDA graph when N > 1")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
@@ -187,7 +185,7 @@ def main():
     devb = {k: v.to(dev) for k, v in host.items()}
     loss_host = torch.zeros(1).pin_memory()
 
-    def step(b):
+    def fwd_bwd(b):
         pred = net(b["image"])
         inter = pred["depth"]["intermediate_depths"]
         lf = crit_d(pred["depth"]["final_depth"], b["gt_final"])
@@ -197,8 +195,15 @@ def main():
         ls = crit_s(fs, b["gt_seg"]) if fs is not None else 0
         loss = (lf + l4 + l3 + 0.2 * ls) / 3.4
         loss.backward()
+        return loss
+
+    def opt_step():
         opt.step()
         opt.zero_grad(set_to_none=True)
+
+    def step(b):
+        loss = fwd_bwd(b)
+        opt_step()
         return loss
 
     def e2e_step():
@@ -212,14 +217,14 @@ def main():
         torch.cuda.synchronize()
 
     from camradepth_b200.graphs import GraphedTrainStep
-    use_graph = (not a.no_graph) and (world == 1 or a.graph_multi == 1)
+    use_graph = not a.no_graph
     for _ in range(a.warmup):
         step(devb)
     eng = model._engines[a.precision]
     n0 = ops.launch_count()
     step(devb)
     launches_per_step = ops.launch_count() - n0
-    if use_graph:
+    if use_graph and world == 1:
         # the whole step (fwd + losses + bwd + optimizer) is captured once and replayed; the optimizer's
         # host-side bookkeeping (step counters, device-resident step size) runs before each replay
         gstep = GraphedTrainStep(step, devb, warmup=0)
@@ -231,6 +236,31 @@ def main():
         def run_e2e():
             opt.advance_for_replay()
             loss = gstep(host)                       # H2D copies of the pinned host batch into the static inputs
+            loss_host.copy_(loss.detach().view(1), non_blocking=True)
+    elif use_graph:
+        # N > 1: graph A = fwd + losses + bwd, then ONE NCCL all-reduce of the flat gradient buffer (launched
+        # eagerly: capturing NCCL work inside the graph hangs with this torch/NCCL pair), then graph B = optimizer.
+        # The all-reduce is ~0.3 % of the step, so not overlapping it costs less than eager launch overhead.
+        net.require_backward_grad_sync = False
+        step(devb)                                   # p.grad now lives in the engine's persistent flat buffer
+        g_fb = GraphedTrainStep(fwd_bwd, devb, warmup=0)
+        torch.cuda.synchronize()
+        g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_opt):
+            opt_step()
+
+        def _replay(batch):
+            opt.advance_for_replay()
+            loss = g_fb(batch)
+            dist.all_reduce(eng._flat_own, op=dist.ReduceOp.AVG)
+            g_opt.replay()
+            return loss
+
+        def run_resident():
+            return _replay(None)
+
+        def run_e2e():
+            loss = _replay(host)
             loss_host.copy_(loss.detach().view(1), non_blocking=True)
     else:
         def run_resident():
@@ -291,7 +321,8 @@ def main():
                                    f"diffGradNorm, DropPath/Dropout2d on), batch {B}/GPU, 192x416 (nominal 192x400: the "
                                    f"reference cannot run 400-wide inputs), RGB+radar 7ch",
                        "global_batch": world * B, "parallelism": f"dp{world}",
-                       "launch": "one CUDA graph per step" if use_graph else "eager kernel launches",
+                       "launch": ("one CUDA graph per step" if world == 1 else "two CUDA graphs per step around one NCCL all-reduce")
+                       if use_graph else "eager kernel launches",
                        "l2": "no flush: per-step working set (several GB of activations) is far larger than the 126 MB L2",
                        "step_flops": FLOPS_TRAIN_PER_SAMPLE.get(a.variant, 0) * B,
                        "step_tensor_frac_of_" + pk_src: (value / world) * FLOPS_TRAIN_PER_SAMPLE.get(a.variant, 0) / 1e12 / peak},
