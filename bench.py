@@ -242,7 +242,9 @@ def main():
         # eagerly: capturing NCCL work inside the graph hangs with this torch/NCCL pair), then graph B = optimizer.
         # The all-reduce is ~0.3 % of the step, so not overlapping it costs less than eager launch overhead.
         net.require_backward_grad_sync = False
-        step(devb)                                   # p.grad now lives in the engine's persistent flat buffer
+        fwd_bwd(devb)                                # p.grad now lives in the engine's persistent flat buffer
+        dist.all_reduce(eng._flat_own, op=dist.ReduceOp.AVG)
+        opt_step()
         g_fb = GraphedTrainStep(fwd_bwd, devb, warmup=0)
         torch.cuda.synchronize()
         g_opt = torch.cuda.CUDAGraph()
