@@ -28,6 +28,9 @@ FLOPS_FWD_PER_SAMPLE = {"base": 150.5e9}          # SURVEY.md §8(d), conv/GEMM 
 FLOPS_TRAIN_PER_SAMPLE = {"base": 451.6e9}
 DOMINANT = "depth_upsample.4.conv.layers.2.model.0.weight"   # 3x3, Cin 296 -> 128 at full resolution
 DOMINANT_FLOPS_PER_SAMPLE = 2.0 * 192 * 416 * 128 * 9 * 296  # as written in the reference (54.5 GF)
+# dram__bytes_read.sum + dram__bytes_write.sum of that launch at batch 32, from the committed `ncu --set full`
+# capture profiles/r1_ncu_full_summary.md (algorithmic bytes: 2.168e9)
+DOMINANT_TRAFFIC_B32 = 2.141e9
 
 
 def peaks():
@@ -331,9 +334,12 @@ def main():
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "tensor", "kernel": "conv implicit-GEMM fwd, depth_upsample[4] layer 2 (M=B*79872, N=128, K=2664)",
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_halo_kernel: tcgen05 implicit-GEMM 3x3 conv fwd, depth_upsample[4] layer 2 "
+                                   "(M=B*79872 pixels, N=128, K=9*296)",
                          "achieved": dom_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (dom_tflops / peak) if dom_tflops else None, "traffic": None,
+                         "frac": (dom_tflops / peak) if dom_tflops else None,
+                         "traffic": DOMINANT_TRAFFIC_B32 * B / 32.0,
+                         "algorithmic_bytes": (192 * 416 * (296 + 128) * 2.0) * B + 128 * 9 * 296 * 2.0,
                          "peak_source": pk_src + " (bf16_tflops_sustained)", "launch_ms": dom_ms,
                          "launches_timed": len(dom)},
         }
