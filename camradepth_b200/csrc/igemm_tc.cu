@@ -284,9 +284,16 @@ constexpr int HL_A_BYTES = 18 * 16 * 128;
 constexpr int HL_A_STAGES = 3;
 constexpr int HL_B_MAX = 6;
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent: one CTA per SM walks the tile list; the accumulator pair is double-buffered in TMEM (2 x 2 x 128
+// columns) so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const TcParams p, const float* __restrict__ bias, void* __restrict__ yv) {
+                    const TcParams p, const float* __restrict__ bias, void* __restrict__ yv, int total_tiles,
+                    int ntile_n) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int nB = p.nstages;                       // weight ring depth
@@ -295,28 +302,22 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const uint32_t bars = ring_b + nB * b_bytes;
   const uint32_t bar_fullA = bars, bar_emptyA = bars + 8 * HL_A_STAGES;
   const uint32_t bar_fullB = bars + 16 * HL_A_STAGES, bar_emptyB = bar_fullB + 8 * HL_B_MAX;
-  const uint32_t bar_tmem = bar_emptyB + 8 * HL_B_MAX;
-  const uint32_t tmem_slot = bar_tmem + 8;
+  const uint32_t bar_tfull = bar_emptyB + 8 * HL_B_MAX, bar_tempty = bar_tfull + 16;
+  const uint32_t tmem_slot = bar_tempty + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * p.bn;
-  int t = blockIdx.x;
-  const int tw = t % p.tiles_w; t /= p.tiles_w;
-  const int th = t % p.tiles_h; t /= p.tiles_h;
-  const int b = t, oh0 = th * 16, ow0 = tw * 16;
-  const int nA = p.kchunks * 3;                   // (chunk, kw) activation stages
-  const uint32_t sub_stride = p.bn > 128 ? 256u : 128u;      // TMEM columns between the two accumulators
+  const int nA = p.kchunks * 3;                   // (chunk, kw) activation stages per tile
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < HL_A_STAGES; s++) { mbar_init(bar_fullA + 8 * s, 1); mbar_init(bar_emptyA + 8 * s, 1); }
     for (int s = 0; s < nB; s++) { mbar_init(bar_fullB + 8 * s, 1); mbar_init(bar_emptyB + 8 * s, 1); }
-    mbar_init(bar_tmem, 1);
+    for (int s = 0; s < 2; s++) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -326,68 +327,94 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      int jb = 0;
-      for (int it = 0; it < nA; it++) {
-        const int sa = it % HL_A_STAGES;
-        const int chunk = it / 3, kw = it - chunk * 3, c0 = chunk * TC_BK;
-        mbar_wait(bar_emptyA + 8 * sa, ((it / HL_A_STAGES) & 1) ^ 1);
-        mbar_expect_tx(bar_fullA + 8 * sa, HL_A_BYTES);
-        const int dw = p.transposed ? (1 - kw) : (kw - 1);
-        tma_load_4d(base + sa * HL_A_BYTES, &map_a, bar_fullA + 8 * sa, c0, ow0 + dw, oh0 - 1, b);
-        for (int kh = 0; kh < 3; kh++, jb++) {
-          const int sb = jb % nB;
-          mbar_wait(bar_emptyB + 8 * sb, ((jb / nB) & 1) ^ 1);
-          mbar_expect_tx(bar_fullB + 8 * sb, b_bytes);
-          tma_load_2d(ring_b + sb * b_bytes, &map_b, bar_fullB + 8 * sb, (kh * 3 + kw) * p.Cin + c0, n0);
+      int ia = 0, jb = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int n0 = (t % ntile_n) * p.bn; t /= ntile_n;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; t /= p.tiles_h;
+        const int b = t, oh0 = th * 16, ow0 = tw * 16;
+        for (int it = 0; it < nA; it++, ia++) {
+          const int sa = ia % HL_A_STAGES;
+          const int chunk = it / 3, kw = it - chunk * 3, c0 = chunk * TC_BK;
+          mbar_wait(bar_emptyA + 8 * sa, ((ia / HL_A_STAGES) & 1) ^ 1);
+          mbar_expect_tx(bar_fullA + 8 * sa, HL_A_BYTES);
+          const int dw = p.transposed ? (1 - kw) : (kw - 1);
+          tma_load_4d(base + sa * HL_A_BYTES, &map_a, bar_fullA + 8 * sa, c0, ow0 + dw, oh0 - 1, b);
+          for (int kh = 0; kh < 3; kh++, jb++) {
+            const int sb = jb % nB;
+            mbar_wait(bar_emptyB + 8 * sb, ((jb / nB) & 1) ^ 1);
+            mbar_expect_tx(bar_fullB + 8 * sb, b_bytes);
+            tma_load_2d(ring_b + sb * b_bytes, &map_b, bar_fullB + 8 * sb, (kh * 3 + kw) * p.Cin + c0, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, p.bn);
-      int jb = 0;
-      for (int it = 0; it < nA; it++) {
-        const int sa = it % HL_A_STAGES;
-        mbar_wait(bar_fullA + 8 * sa, (it / HL_A_STAGES) & 1);
-        const uint32_t a_base = base + sa * HL_A_BYTES;
-        for (int kh = 0; kh < 3; kh++, jb++) {
-          const int sb = jb % nB;
-          mbar_wait(bar_fullB + 8 * sb, (jb / nB) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const int rowoff = p.transposed ? (2 - kh) : kh;          // halo row of the tap inside the 18-row box
-          const uint64_t bd = umma_desc_kmajor_sw128(ring_b + sb * b_bytes);
+      int ia = 0, jb = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+        const int buf = tcount & 1;
+        mbar_wait(bar_tempty + 8 * buf, ((tcount >> 1) & 1) ^ 1);      // epilogue has drained this buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_base + (uint32_t)buf * 256u;
+        for (int it = 0; it < nA; it++, ia++) {
+          const int sa = ia % HL_A_STAGES;
+          mbar_wait(bar_fullA + 8 * sa, (ia / HL_A_STAGES) & 1);
+          const uint32_t a_base = base + sa * HL_A_BYTES;
+          for (int kh = 0; kh < 3; kh++, jb++) {
+            const int sb = jb % nB;
+            mbar_wait(bar_fullB + 8 * sb, (jb / nB) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int rowoff = p.transposed ? (2 - kh) : kh;          // halo row of the tap inside the 18-row box
+            const uint64_t bd = umma_desc_kmajor_sw128(ring_b + sb * b_bytes);
 #pragma unroll
-          for (int sub = 0; sub < 2; sub++) {
-            const uint64_t ad = umma_desc_kmajor_sw128(a_base + (uint32_t)(rowoff + 8 * sub) * 2048u);
+            for (int sub = 0; sub < 2; sub++) {
+              const uint64_t ad = umma_desc_kmajor_sw128(a_base + (uint32_t)(rowoff + 8 * sub) * 2048u);
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; k++)
-              umma_bf16_ss(tmem_base + sub * sub_stride, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
-                           (it | kh | k) != 0);
+              for (int k = 0; k < TC_BK / 16; k++)
+                umma_bf16_ss(acc + sub * 128u, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
+                             (it | kh | k) != 0);
+            }
+            umma_commit(bar_emptyB + 8 * sb);
           }
-          umma_commit(bar_emptyB + 8 * sb);
+          umma_commit(bar_emptyA + 8 * sa);
         }
-        umma_commit(bar_emptyA + 8 * sa);
+        umma_commit(bar_tfull + 8 * buf);
       }
-      umma_commit(bar_tmem);
     }
   } else {
     const int lg = warp & 3;
     const int row = lg * 32 + lane;
-    mbar_wait(bar_tmem, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+      int t = tile;
+      const int n0 = (t % ntile_n) * p.bn; t /= ntile_n;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;
+      const int b = t, oh0 = th * 16, ow0 = tw * 16;
+      const int buf = tcount & 1;
+      mbar_wait(bar_tfull + 8 * buf, (tcount >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-    for (int sub = 0; sub < 2; sub++) {
-      const int ty = (row >> 4) + 8 * sub, tx = row & 15;
-      const int oh = oh0 + ty, ow = ow0 + tx;
-      const bool ok = oh < p.Ho && ow < p.Wo;
-      const long long pix = ((long long)b * p.Ho + oh) * p.Wo + ow;
-      epilogue_rows(p, tmem_base + ((uint32_t)(lg * 32) << 16) + sub * sub_stride, n0, ok, pix, bias, yv);
+      for (int sub = 0; sub < 2; sub++) {
+        const int ty = (row >> 4) + 8 * sub, tx = row & 15;
+        const int oh = oh0 + ty, ow = ow0 + tx;
+        const bool ok = oh < p.Ho && ow < p.Wo;
+        const long long pix = ((long long)b * p.Ho + oh) * p.Wo + ow;
+        epilogue_rows(p, tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * 256u + sub * 128u, n0, ok, pix,
+                      bias, yv);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);          // 4 epilogue warps -> buffer free
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -472,15 +499,22 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
   static int use_halo = -1;
   if (use_halo < 0) { const char* e = getenv("CAMRADEPTH_TC_HALO"); use_halo = (e && e[0] == '0') ? 0 : 1; }
   if (use_halo && d->KH == 3 && d->H % 16 == 0 && d->W >= 16 && d->Cin >= 136 && d->Cout >= 64) {
+    static int num_sms = 0;
+    if (!num_sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+      if (num_sms <= 0) num_sms = 148;
+    }
     static bool halo_attr = false;
     if (!halo_attr) {
       cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return (int)e;
       halo_attr = true;
     }
-    const int ntile = (d->Cout + 159) / 160;
+    const int ntile = (d->Cout + 127) / 128;          // accumulators are 128 TMEM columns each, double buffered
     p.bn = ((d->Cout + ntile - 1) / ntile + 15) / 16 * 16;
-    p.tmem_cols = p.bn <= 128 ? 256 : 512;
+    p.tmem_cols = 512;
     const int b_bytes = p.bn * 128;
     p.nstages = (224 * 1024 - HL_A_STAGES * HL_A_BYTES - 2048) / b_bytes;
     if (p.nstages > HL_B_MAX) p.nstages = HL_B_MAX;
@@ -499,7 +533,9 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
     rc = make_map(&map_b, w, 2, dimsb, strb, boxb);
     if (rc) return rc;
     const int smem = HL_A_STAGES * HL_A_BYTES + p.nstages * b_bytes + 1024 + 256;
-    conv_tc_halo_kernel<<<dim3(p.tiles_w * p.tiles_h * d->B, ntile), TC_THREADS, smem, s>>>(map_a, map_b, p, bias, y);
+    const int total_tiles = p.tiles_w * p.tiles_h * d->B * ntile;
+    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    conv_tc_halo_kernel<<<grid, TC_THREADS, smem, s>>>(map_a, map_b, p, bias, y, total_tiles, ntile);
     CRD_LAUNCH_CHECK();
     return 0;
   }
