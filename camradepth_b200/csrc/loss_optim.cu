@@ -171,6 +171,102 @@ __global__ void __launch_bounds__(256) diffgradnorm_kernel(const crd_opt_tensor*
   }
 }
 
+// ------------------------------------------------------------------ test-mode metrics (runner.py:442-492)
+// pred is clipped to [0,1]; both are scaled by max_depth; valid = gt > 0 (and gt >= thr2 for the second set).
+// acc[0..3] = (sum sq, sum abs, sum rel, count) within max range; acc[4..7] = same for gt >= thr2.
+__global__ void depth_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt, float* acc,
+                                     long long n, float max_depth, float thr2) {
+  __shared__ float sh[32];
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) a[j] = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float g = gt[i] * max_depth;
+    if (g > 0.f) {
+      const float p = fminf(fmaxf(pred[i], 0.f), 1.f) * max_depth;
+      const float e = p - g, ae = fabsf(e), re = ae / g;
+      a[0] = fmaf(e, e, a[0]); a[1] += ae; a[2] += re; a[3] += 1.f;
+      if (g >= thr2) { a[4] = fmaf(e, e, a[4]); a[5] += ae; a[6] += re; a[7] += 1.f; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const float r = block_sum(a[j], sh);
+    if (threadIdx.x == 0) atomicAdd(acc + j, r);
+  }
+}
+// out[0..2] = RMSE, MAE, REL (max range); out[3..5] = same (second range)
+__global__ void depth_metrics_finalize_kernel(const float* __restrict__ acc, float* __restrict__ out) {
+  for (int s = 0; s < 2; s++) {
+    const float c = acc[4 * s + 3];
+    out[3 * s + 0] = sqrtf(acc[4 * s + 0] / c);
+    out[3 * s + 1] = acc[4 * s + 1] / c;
+    out[3 * s + 2] = acc[4 * s + 2] / c;
+  }
+}
+// conf[t][p] += 1 for every pixel with target t != ignore_index and p = argmax_c logits
+__global__ void confusion_kernel(const float* __restrict__ logits, const long long* __restrict__ target, float* conf,
+                                 int B, int C, long long HW, int ignore_index) {
+  const long long total = (long long)B * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long t = target[i];
+    if (t == ignore_index || t < 0 || t >= C) continue;
+    const long long b = i / HW, r = i - b * HW;
+    const float* lp = logits + b * C * HW + r;
+    float best = lp[0];
+    int bi = 0;
+    for (int c = 1; c < C; c++) { const float v = lp[c * HW]; if (v > best) { best = v; bi = c; } }
+    atomicAdd(conf + t * C + bi, 1.f);
+  }
+}
+
+// ------------------------------------------------------------------ input pipeline (dataloader.py:213-245)
+// inverse-normalised lidar GT: g = d > 0 ? (max_depth - min(d, max_depth)) / max_depth : 0
+__global__ void gt_normalize_kernel(const float* __restrict__ d, float* __restrict__ g, long long n, float max_depth) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float v = fminf(fmaxf(d[i], 0.f), max_depth);
+    g[i] = v > 0.f ? (max_depth - v) / max_depth : 0.f;
+  }
+}
+// zero-ignoring 3x3 stride-2 pad-1 min-pool (zeros count as "no measurement"; 255 never survives)
+__global__ void minpool_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int Ho, int Wo) {
+  const long long total = (long long)B * Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ow = (int)(i % Wo), oh = (int)((i / Wo) % Ho);
+    const long long b = i / ((long long)Wo * Ho);
+    float m = 255.f;
+    for (int dh = -1; dh <= 1; dh++) {
+      const int h = 2 * oh + dh;
+      if (h < 0 || h >= H) continue;
+      for (int dw = -1; dw <= 1; dw++) {
+        const int w = 2 * ow + dw;
+        if (w < 0 || w >= W) continue;
+        const float v = x[(b * H + h) * W + w];
+        m = fminf(m, v == 0.f ? 255.f : v);
+      }
+    }
+    y[i] = m == 255.f ? 0.f : m;
+  }
+}
+// uint8 HWC image -> fp32 channels [c0, c0+3) of an NCHW batch tensor, (v/255 - mean[c]) / std[c]
+__global__ void image_normalize_kernel(const unsigned char* __restrict__ img, float* __restrict__ out, int B, int H,
+                                       int W, int Ctot, float m0, float m1, float m2, float s0, float s1, float s2) {
+  const long long hw = (long long)H * W, total = (long long)B * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / hw, r = i - b * hw;
+    const unsigned char* p = img + i * 3;
+    float* o = out + b * Ctot * hw + r;
+    o[0] = ((float)p[0] * (1.f / 255.f) - m0) / s0;
+    o[hw] = ((float)p[1] * (1.f / 255.f) - m1) / s1;
+    o[2 * hw] = ((float)p[2] * (1.f / 255.f) - m2) / s2;
+  }
+}
+
 inline int red_blocks(long long n) {
   long long b = (n + 1023) / 1024;
   return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
@@ -228,6 +324,49 @@ extern "C" int crd_diffgradnorm_update(const crd_opt_tensor* table, const crd_op
   if (nchunks == 0) return 0;
   diffgradnorm_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(table, chunks, sumsq, egn_in, egn_out, step_size,
                                                                  beta1, beta2, eps);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int crd_depth_metrics(const float* pred, const float* gt, float* acc, float* out, long long n,
+                                 float max_depth, float thr2, crd_stream_t stream) {
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(acc, 0, 8 * sizeof(float), s);
+  depth_metrics_kernel<<<red_blocks(n), 256, 0, s>>>(pred, gt, acc, n, max_depth, thr2);
+  CRD_LAUNCH_CHECK();
+  depth_metrics_finalize_kernel<<<1, 1, 0, s>>>(acc, out);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_confusion(const float* logits, const long long* target, float* conf, int B, int C, long long HW,
+                             int ignore_index, crd_stream_t stream) {
+  if ((long long)B * HW == 0) return 0;
+  confusion_kernel<<<red_blocks((long long)B * HW), 256, 0, (cudaStream_t)stream>>>(logits, target, conf, B, C, HW,
+                                                                                    ignore_index);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_gt_normalize(const float* d, float* g, long long n, float max_depth, crd_stream_t stream) {
+  if (n == 0) return 0;
+  gt_normalize_kernel<<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>(d, g, n, max_depth);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_minpool3x3s2(const float* x, float* y, int B, int H, int W, crd_stream_t stream) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)B * Ho * Wo;
+  if (total == 0) return 0;
+  minpool_kernel<<<red_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, Ho, Wo);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_image_normalize(const unsigned char* img, float* out, int B, int H, int W, int Ctot,
+                                   const float* mean3_host, const float* std3_host, crd_stream_t stream) {
+  const long long total = (long long)B * H * W;
+  if (total == 0) return 0;
+  image_normalize_kernel<<<red_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+      img, out, B, H, W, Ctot, mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0], std3_host[1], std3_host[2]);
   CRD_LAUNCH_CHECK();
   return 0;
 }

@@ -193,6 +193,24 @@ CRD_API int crd_ce_bwd(const float* logits, const long long* target, const float
 /* out[0] = acc[0]/acc[1] ; (focal) out[0] = (1-exp(-ce))^gamma * ce ; (rmse) out[1] = sqrt(acc[2]/acc[1]) */
 CRD_API int crd_loss_finalize(const float* acc, float* out, int kind, float gamma, crd_stream_t stream);
 
+/* ---------------------------------------------------------------- test-mode metrics (runner.py:442-492)
+ * pred clipped to [0,1], both scaled by max_depth, valid = gt > 0; second set additionally gt >= thr2 (the
+ * "<= 50 m" subset in inverse-depth space).  acc: 8 floats scratch, out[6] = RMSE, MAE, REL x 2. */
+CRD_API int crd_depth_metrics(const float* pred, const float* gt, float* acc, float* out, long long n,
+                      float max_depth, float thr2, crd_stream_t stream);
+/* conf[t][p] += #pixels with label t (!= ignore_index) predicted as p = argmax_c logits (NCHW) -- IoU input */
+CRD_API int crd_confusion(const float* logits, const long long* target, float* conf, int B, int C, long long HW,
+                  int ignore_index, crd_stream_t stream);
+
+/* ---------------------------------------------------------------- input pipeline (dataloader.py:202-257)
+ * inverse-normalised lidar GT, its zero-ignoring 3x3/s2 min-pool pyramid, ImageNet normalisation of the
+ * uint8 HWC camera image into channels [0,3) of the (B,Ctot,H,W) fp32 network input.
+ * mean3 / std3 are HOST pointers to 3 floats. */
+CRD_API int crd_gt_normalize(const float* d, float* g, long long n, float max_depth, crd_stream_t stream);
+CRD_API int crd_minpool3x3s2(const float* x, float* y, int B, int H, int W, crd_stream_t stream);
+CRD_API int crd_image_normalize(const unsigned char* img, float* out, int B, int H, int W, int Ctot,
+                        const float* mean3, const float* std3, crd_stream_t stream);
+
 /* ---------------------------------------------------------------- diffGradNorm (diffGradNorm.py:41-113)
  * multi-tensor: table rows describe (param, grad, exp_avg, exp_avg_sq, previous_grad, numel). */
 typedef struct {

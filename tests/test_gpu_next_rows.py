@@ -1,0 +1,141 @@
+"""test-mode metrics, input pipeline, training-step driver, checkpoint layout --
+each against the reference semantics restated with plain torch ops / the CPU oracle."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.test_gpu_ops import rel
+
+pytestmark = pytest.mark.gpu
+dev = torch.device("cuda:0")
+
+
+def test_depth_metrics_match_reference_loop():
+    """Restates runner.py:442-492 with torch ops on the same tensors."""
+    from camradepth_b200 import depth_metrics
+    torch.manual_seed(0)
+    pred = torch.rand(1, 1, 64, 96, device=dev) * 1.2 - 0.1
+    gt = torch.rand(1, 1, 64, 96, device=dev) * (torch.rand(1, 1, 64, 96, device=dev) < 0.3)
+    m = depth_metrics(pred, gt)
+    p = torch.clip(pred.squeeze(), 0, 1) * 100
+    g = gt.squeeze() * 100
+    g = g.clone(); g[g > 100] = 0
+    idx = torch.where(g > 0)
+    err = p[idx] - g[idx]
+    ref = {"mae_100": err.abs().mean(), "rmse_100": err.pow(2).mean().sqrt(), "rel_100": (err.abs() / g[idx]).mean()}
+    g[g < 50] = 0
+    idx = torch.where(g > 0)
+    err = p[idx] - g[idx]
+    ref.update({"mae_50": err.abs().mean(), "rmse_50": err.pow(2).mean().sqrt(), "rel_50": (err.abs() / g[idx]).mean()})
+    for k, v in ref.items():
+        assert abs(float(m[k]) - float(v)) < 1e-4 * max(1.0, abs(float(v))), k
+
+
+def test_mean_iou():
+    from camradepth_b200.metrics import confusion_matrix, mean_iou
+    torch.manual_seed(1)
+    lg = torch.randn(2, 21, 32, 48, device=dev)
+    t = torch.randint(0, 21, (2, 32, 48), device=dev)
+    t[torch.rand(2, 32, 48, device=dev) < 0.1] = 255
+    conf = confusion_matrix(lg, t)
+    pr = lg.argmax(1)
+    valid = t != 255
+    ref = torch.zeros(21, 21, device=dev)
+    ref.index_put_((t[valid], pr[valid]), torch.ones(int(valid.sum()), device=dev), accumulate=True)
+    assert torch.equal(conf, ref)
+    inter = ref.diag(); union = ref.sum(0) + ref.sum(1) - inter
+    assert abs(float(mean_iou(lg, t)) - float((inter / union).mean())) < 1e-6
+
+
+def test_input_pipeline_matches_dataloader_contract():
+    from camradepth_b200.preprocess import normalize_image, gt_pyramid, IMAGENET_MEAN, IMAGENET_STD
+    from oracle import camradepth_oracle as O
+    torch.manual_seed(2)
+    img = torch.randint(0, 256, (2, 64, 96, 3), dtype=torch.uint8, device=dev)
+    x = torch.zeros(2, 7, 64, 96, device=dev)
+    normalize_image(img, x)
+    ref = (img.float() / 255 - torch.tensor(IMAGENET_MEAN, device=dev)) / torch.tensor(IMAGENET_STD, device=dev)
+    assert rel(x[:, :3], ref.permute(0, 3, 1, 2)) < 1e-6 and float(x[:, 3:].abs().max()) == 0
+    depth = torch.rand(2, 1, 64, 96, device=dev) * 130 * (torch.rand(2, 1, 64, 96, device=dev) < 0.2)
+    g0, g1, g2 = gt_pyramid(depth)
+    d = depth.cpu().clamp(0, 100)
+    gn = torch.where(d > 0, (100 - d) / 100, torch.zeros_like(d))        # dataloader.py:240-245
+    assert rel(g0.cpu(), gn) < 1e-6
+    m1 = O.minpool(gn)                                                   # dataloader.py:213-222
+    assert torch.allclose(g1.cpu(), m1) and torch.allclose(g2.cpu(), O.minpool(m1))
+
+
+def test_train_step_driver_matches_reference_loop():
+    """Three micro-batches with update_interval=2 and OneCycleLR, fp32 mode, against the oracle driven by the
+    reference's loop logic (runner.py:166-270)."""
+    import camradepth_b200 as C
+    from camradepth_b200.synthetic import make_batch
+    from oracle import camradepth_oracle as O
+    torch.set_num_threads(os.cpu_count() or 8)
+    cfg = O.Cfg("supervised_seg")
+    sd = O.init_state_dict(cfg, seed=2, perturb=0.02)
+    C.set_model("supervised_seg")
+    model = C.CamRaDepth(precision="fp32")
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    UI, NB, LR = 2, 3, 1e-3
+    opt = C.diffGradNorm(model.parameters(), lr=LR)
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=LR, steps_per_epoch=NB, epochs=2, div_factor=2, pct_start=0.15)
+    ts = C.TrainStep(model, opt, sched, update_interval=UI, supervised_seg=True, batches_per_epoch=NB)
+    batches = [make_batch(1, 64, 64, seed=20 + i) for i in range(NB)]
+    ts.start_epoch()
+    stepped = []
+    for b in batches:
+        _, st = ts({k: v.to(dev) for k, v in b.items()})
+        stepped.append(st)
+    assert stepped == [False, True, True]            # boundary at i+1 == 2 and at the last batch of the epoch
+    stats = ts.stats()
+    # ---- reference loop on the oracle
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    dummy = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=LR)
+    rs = torch.optim.lr_scheduler.OneCycleLR(dummy, max_lr=LR, steps_per_epoch=NB, epochs=2, div_factor=2, pct_start=0.15)
+    states = {k: {} for k in p}
+    finals = []
+    for i, b in enumerate(batches):
+        pred = O.forward(p, cfg, b["image"])
+        loss, parts = O.training_loss(pred, b["gt_final"], b["gt_s4"], b["gt_s3"], b["gt_seg"], cfg, update_interval=UI)
+        finals.append(float(parts["final"]))
+        loss.backward()
+        if (i + 1) % UI == 0 or (i + 1) == NB:
+            lr = dummy.param_groups[0]["lr"]
+            with torch.no_grad():
+                for k, v in p.items():
+                    if v.grad is not None:
+                        O.diffgradnorm_step(v, v.grad, states[k], lr=lr)
+                        v.grad = None
+        if (i + 1) > UI:
+            rs.step()
+    assert abs(opt.param_groups[0]["lr"] - dummy.param_groups[0]["lr"]) < 1e-12
+    worst = max(rel(q.detach().cpu(), p[n].detach()) for n, q in model.named_parameters())
+    assert worst < 2e-5, worst
+    assert abs(stats["loss_depth_final"] - sum(finals) / NB) < 1e-5
+    C.set_model("base")
+
+
+def test_checkpoint_layout_roundtrip(tmp_path):
+    import camradepth_b200 as C
+    from camradepth_b200.synthetic import make_batch
+    C.set_model("base")
+    torch.manual_seed(3)
+    m = C.CamRaDepth(precision="bf16").to(dev).eval()
+    opt = C.diffGradNorm(m.parameters(), lr=6e-5)
+    b = {k: v.to(dev) for k, v in make_batch(1, 64, 64, seed=1).items()}
+    C.MaskedSmoothL1Loss()(m(b["image"])["depth"]["final_depth"], b["gt_final"]).backward()
+    opt.step()
+    path = str(tmp_path / "ck.pth")
+    C.save_checkpoint(path, torch.nn.DataParallel(m) if False else m, opt, 6e-5, 1)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert sorted(ck.keys()) == ["lr", "optimizer", "state_dict", "steps"]
+    st0 = ck["optimizer"]["state"][0]
+    assert sorted(st0.keys()) == ["exp_avg", "exp_avg_sq", "exp_grad_norm", "previous_grad", "step"]
+    assert len(ck["optimizer"]["state"]) == 881 and st0["exp_avg"].shape == m.state_dict()["dest_encoder.patch_embed1.proj.weight"].shape
+    m2 = C.CamRaDepth(precision="bf16")
+    C.load_checkpoint_with_shape_match(m2, {"module." + k: v for k, v in ck["state_dict"].items()})
+    assert all(torch.equal(a.cpu(), b2) for a, b2 in zip(m.state_dict().values(), m2.state_dict().values()))
