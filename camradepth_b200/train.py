@@ -49,8 +49,8 @@ class TrainStep:
         loss, parts = self.loss(pred, batch)
         with torch.no_grad():
             rmse = torch.sqrt(self.mse(pred["depth"]["final_depth"], batch["gt_final"])) * args.get("max_depth", 100)
-            s = torch.stack([parts["final"].detach(), parts["s4"].detach(), rmse,
-                             torch.as_tensor(parts["seg"], device=rmse.device, dtype=torch.float32).detach()])
+            seg = parts["seg"].detach() if torch.is_tensor(parts["seg"]) else torch.zeros_like(rmse)
+            s = torch.stack([parts["final"].detach(), parts["s4"].detach(), rmse, seg])
             self._stats = s if self._stats is None else self._stats + s
         loss.backward()
         last = self.batches_per_epoch is not None and (self.i + 1) == self.batches_per_epoch
