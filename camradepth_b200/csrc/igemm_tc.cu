@@ -418,6 +418,108 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------ persistent 1x1 GEMM
+// The encoder's pointwise contractions have short K (64..1024): a one-tile CTA spends more time in its prologue
+// (barrier init, TMEM allocation, first TMA round trip) and epilogue than in its 2..32 MMAs.  This variant keeps
+// one CTA per SM alive over the tile list, lets the TMA producer run ahead across tiles and double-buffers the
+// accumulator in TMEM, so prologue cost is paid once and the epilogue (HBM-bound output write) overlaps the MMAs.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                          const TcParams p, const float* __restrict__ bias, void* __restrict__ yv, int total_tiles,
+                          int ntile_n) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int NS = p.nstages;
+  const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
+  const uint32_t bars = base + NS * stage_bytes;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * TC_MAX_STAGES;
+  const uint32_t bar_tfull = bars + 16 * TC_MAX_STAGES, bar_tempty = bar_tfull + 16;
+  const uint32_t tmem_slot = bar_tempty + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk = p.kchunks;
+  const uint32_t buf_stride = (uint32_t)p.tmem_cols / 2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx = TC_A_BYTES + (uint32_t)p.bn * TC_BK * 2;
+      int ia = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % ntile_n) * p.bn;
+        const int m0 = (tile / ntile_n) * TC_BM;
+        for (int it = 0; it < nk; it++, ia++) {
+          const int s = ia % NS;
+          mbar_wait(bar_empty + 8 * s, ((ia / NS) & 1) ^ 1);
+          const uint32_t sa = base + s * stage_bytes, sb = sa + TC_A_BYTES;
+          mbar_expect_tx(bar_full + 8 * s, tx);
+          tma_load_2d(sa, &map_a, bar_full + 8 * s, it * TC_BK, m0);
+          tma_load_2d(sb, &map_b, bar_full + 8 * s, it * TC_BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.bn);
+      int ia = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+        const int buf = tcount & 1;
+        mbar_wait(bar_tempty + 8 * buf, ((tcount >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_base + (uint32_t)buf * buf_stride;
+        for (int it = 0; it < nk; it++, ia++) {
+          const int s = ia % NS;
+          mbar_wait(bar_full + 8 * s, (ia / NS) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = base + s * stage_bytes, sb = sa + TC_A_BYTES;
+          const uint64_t ad = umma_desc_kmajor_sw128(sa), bd = umma_desc_kmajor_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; k++)
+            umma_bf16_ss(acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) != 0);
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+      const int n0 = (tile % ntile_n) * p.bn;
+      const long long pix = (long long)(tile / ntile_n) * TC_BM + row;
+      const int buf = tcount & 1;
+      mbar_wait(bar_tfull + 8 * buf, (tcount >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      epilogue_rows(p, tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * buf_stride, n0, pix < p.P, pix, bias,
+                    yv);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+  }
+}
+
 // ------------------------------------------------------------------ host side: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -542,6 +644,39 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
     const int total_tiles = p.tiles_w * p.tiles_h * d->B * ntile;
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
     conv_tc_halo_kernel<<<grid, TC_THREADS, smem, s>>>(map_a, map_b, p, bias, y, total_tiles, ntile);
+    CRD_LAUNCH_CHECK();
+    return 0;
+  }
+  static int use_pgemm = -1;
+  if (use_pgemm < 0) { const char* e = getenv("CAMRADEPTH_TC_PGEMM"); use_pgemm = (e && e[0] == '0') ? 0 : 1; }
+  if (use_pgemm && p.flat) {
+    static bool pg_attr = false;
+    static int pg_sms = 148;
+    if (!pg_attr) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           227 * 1024);
+      if (e != cudaSuccess) return (int)e;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&pg_sms, cudaDevAttrMultiProcessorCount, dev);
+      if (pg_sms <= 0) pg_sms = 148;
+      pg_attr = true;
+    }
+    const int ntile = (d->Cout + 255) / 256;
+    p.bn = ((d->Cout + ntile - 1) / ntile + 15) / 16 * 16;
+    p.tmem_cols = p.bn <= 128 ? 256 : 512;               // two accumulator buffers
+    p.stage_bytes = TC_A_BYTES + p.bn * TC_BK * 2;
+    p.nstages = (200 * 1024) / p.stage_bytes;
+    if (p.nstages > TC_MAX_STAGES) p.nstages = TC_MAX_STAGES;
+    const int smem = p.nstages * p.stage_bytes + 1024 + 256;
+    cuuint64_t dimsb[2] = {(cuuint64_t)Ktot, (cuuint64_t)d->Cout};
+    cuuint64_t strb[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t boxb[2] = {TC_BK, (cuuint32_t)p.bn};
+    rc = make_map(&map_b, w, 2, dimsb, strb, boxb);
+    if (rc) return rc;
+    const int total_tiles = crd_div_up(P, TC_BM) * ntile;
+    const int grid = total_tiles < pg_sms ? total_tiles : pg_sms;
+    gemm_tc_persistent_kernel<<<grid, TC_THREADS, smem, s>>>(map_a, map_b, p, bias, y, total_tiles, ntile);
     CRD_LAUNCH_CHECK();
     return 0;
   }
