@@ -671,7 +671,8 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
     return 0;
   }
   static int use_pgemm = -1;
-  if (use_pgemm < 0) { const char* e = getenv("CAMRADEPTH_TC_PGEMM"); use_pgemm = (e && e[0] == '0') ? 0 : 1; }
+  // measured slower than two one-tile CTAs per SM (8 epilogue warps instead of 4): opt-in only
+  if (use_pgemm < 0) { const char* e = getenv("CAMRADEPTH_TC_PGEMM"); use_pgemm = (e && e[0] == '1') ? 1 : 0; }
   if (use_pgemm && p.flat) {
     static bool pg_attr = false;
     static int pg_sms = 148;
