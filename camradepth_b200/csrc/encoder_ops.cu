@@ -163,69 +163,47 @@ __global__ void dwconv_bwd_weight_kernel(const T* __restrict__ dy, const T* __re
 }
 
 // ------------------------------------------------------------------ attention score
-// block: 64 tokens of one sample, 4 threads per token.  Per head the token's query row lives in registers and
-// the keys are staged TRANSPOSED in shared memory ([d][key]), so one 16-byte broadcast load feeds four FMAs
-// (four consecutive keys) -- 4 FMA per LDS instead of 1 FMA per 2 LDS.
-constexpr int ATN = 64, AMK = 64, AHD = 64;
+// block: 64 tokens of one sample; loop heads; per head stage q[64][hd] and key chunks k[64][hd] in smem.
+constexpr int ATN = 64, AMK = 64;
 template <typename T>
 __global__ void __launch_bounds__(256) attn_qkmax_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k,
                                                              float* __restrict__ s, unsigned short* __restrict__ idx,
                                                              int B, int N, int M, int C, int heads, float scale) {
-  __shared__ __align__(16) float ks[AHD][AMK];        // [d][key]
+  extern __shared__ float sm[];
   const int hd = C / heads;
+  const int hdp = hd + 1;
+  float* qs = sm;                 // [ATN][hdp]
+  float* ks = sm + ATN * hdp;     // [AMK][hdp]
   const int b = blockIdx.y;
   const int n0 = blockIdx.x * ATN;
   const int tid = threadIdx.x;
   const int nl = tid >> 2, kl = tid & 3;
-  const int n = n0 + nl;
-  const int nc = n < N ? n : N - 1;
   float total = 0.f;
   for (int h = 0; h < heads; h++) {
-    float qr[AHD];
-    const T* qp = q + ((long long)b * N + nc) * C + h * hd;
-#pragma unroll
-    for (int d8 = 0; d8 < AHD / 8; d8++) {
-      float v[8];
-      if (d8 * 8 < hd) load8(qp + d8 * 8, v);
-#pragma unroll
-      for (int j = 0; j < 8; j++) qr[d8 * 8 + j] = (d8 * 8 < hd) ? v[j] : 0.f;
+    __syncthreads();
+    for (int i = tid; i < ATN * hd; i += 256) {
+      const int r = i / hd, dd = i - r * hd;
+      const int n = n0 + r;
+      qs[r * hdp + dd] = (n < N) ? to_f(q[((long long)b * N + n) * C + h * hd + dd]) : 0.f;
     }
     float best = -INFINITY;
     int besti = 0;
     for (int mc = 0; mc < M; mc += AMK) {
       __syncthreads();
-      for (int i = tid; i < AMK * (hd / 8); i += 256) {      // key-major 16-byte loads, transposed store
-        const int r = i / (hd / 8), d8 = i - r * (hd / 8);
+      for (int i = tid; i < AMK * hd; i += 256) {
+        const int r = i / hd, dd = i - r * hd;
         const int m = mc + r;
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = 0.f;
-        if (m < M) load8(k + ((long long)b * M + m) * C + h * hd + d8 * 8, v);
-#pragma unroll
-        for (int j = 0; j < 8; j++) ks[d8 * 8 + j][r] = v[j];
+        ks[r * hdp + dd] = (m < M) ? to_f(k[((long long)b * M + m) * C + h * hd + dd]) : 0.f;
       }
       __syncthreads();
-#pragma unroll
-      for (int g = 0; g < 4; g++) {
-        const int key0 = kl * 16 + g * 4;
-        if (mc + key0 >= M) break;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int dd = 0; dd < AHD; dd++) {
-          if (dd < hd) {
-            const float4 kv = *reinterpret_cast<const float4*>(&ks[dd][key0]);
-            acc.x = fmaf(qr[dd], kv.x, acc.x);
-            acc.y = fmaf(qr[dd], kv.y, acc.y);
-            acc.z = fmaf(qr[dd], kv.z, acc.z);
-            acc.w = fmaf(qr[dd], kv.w, acc.w);
-          }
-        }
-        const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int m = mc + key0 + j;
-          if (m < M && a4[j] > best) { best = a4[j]; besti = m; }
-        }
+      const int mend = min(AMK, M - mc);
+      for (int r = kl; r < mend; r += 4) {
+        float dot = 0.f;
+        const float* qp = qs + nl * hdp;
+        const float* kp = ks + r * hdp;
+#pragma unroll 8
+        for (int dd = 0; dd < hd; dd++) dot = fmaf(qp[dd], kp[dd], dot);
+        if (dot > best) { best = dot; besti = mc + r; }
       }
     }
     // combine the 4 key-lanes (first occurrence wins ties)
@@ -236,8 +214,10 @@ __global__ void __launch_bounds__(256) attn_qkmax_fwd_kernel(const T* __restrict
       if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
     }
     total += best;
+    const int n = n0 + nl;
     if (kl == 0 && n < N) idx[((long long)b * heads + h) * N + n] = (unsigned short)besti;
   }
+  const int n = n0 + nl;
   if (kl == 0 && n < N) s[(long long)b * N + n] = total * scale;
 }
 
@@ -453,10 +433,11 @@ extern "C" int crd_dwconv3x3_bwd_weight(const void* dy, int dtype, const void* x
 extern "C" int crd_attn_qkmax_fwd(const void* q, const void* k, int dtype, float* s, unsigned short* idx, int B,
                                   int N, int M, int C, int heads, float scale, crd_stream_t stream) {
   CRD_REQUIRE(heads > 0 && C % heads == 0 && M >= 1 && M <= 65535);   // idx is uint16
-  CRD_REQUIRE((C / heads) % 8 == 0 && C / heads <= AHD);
   if (B == 0 || N == 0) return 0;
+  const int hd = C / heads;
+  const size_t smem = (size_t)(ATN + AMK) * (hd + 1) * sizeof(float);
   dim3 grid(crd_div_up(N, ATN), B);
-  CRD_DISPATCH_1(dtype, T, attn_qkmax_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dtype, T, attn_qkmax_fwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
                                (const T*)q, (const T*)k, s, idx, B, N, M, C, heads, scale));
   CRD_LAUNCH_CHECK();
   return 0;
