@@ -22,7 +22,7 @@ class ConvDesc(ctypes.Structure):
     """crd_conv_desc"""
     _fields_ = [(n, ctypes.c_int) for n in (
         "B", "H", "W", "Cin", "ldx", "Ho", "Wo", "Cout", "ldy", "KH", "KW", "stride", "pad",
-        "transposed", "in_dtype", "out_dtype", "act", "accumulate", "out_nchw")]
+        "transposed", "in_dtype", "out_dtype", "act", "accumulate", "out_nchw", "w_tap_stride", "w_koff")]
 
 
 def parse_header(path: str = HEADER):

@@ -278,7 +278,7 @@ extern "C" int crd_conv_fwd(const crd_conv_desc* d, const void* x, const void* w
   CRD_REQUIRE(d && x && w && y);
   CRD_REQUIRE(d->Cin % 8 == 0 && d->ldx % 8 == 0);
   CRD_REQUIRE(d->out_nchw || d->ldy % 4 == 0);
-  CRD_REQUIRE(d->stride >= 1);
+  CRD_REQUIRE(d->stride >= 1 && d->w_tap_stride == 0 && d->w_koff == 0);
   const long long M = (long long)d->B * d->Ho * d->Wo;
   if (M == 0) return 0;
   dim3 grid(crd_div_up(M, BM), crd_div_up(d->Cout, BN));

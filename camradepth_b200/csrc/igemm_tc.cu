@@ -34,7 +34,8 @@ struct TcParams {
   long long P;              // total pixels (flat mode)
   int KH, KW, pad, transposed;
   int kchunks;              // ceil(Cin / 64)
-  int Cin;                  // K stride between taps in the packed weights
+  int Cin;                  // channels of A
+  int wstride, woff;        // weight row layout: column of (tap, c) = tap * wstride + woff + c
   int Cout;
   int bn;                   // UMMA N = channels per N tile (multiple of 16, <= 256)
   int nstages, stage_bytes; // smem ring geometry: stage = A (16 KB) + B (bn * 128 B)
@@ -245,7 +246,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int dw = p.transposed ? (p.pad - kw) : (kw - p.pad);
           tma_load_4d(sa, &map_a, bar_full + 8 * s, c0, ow0 + dw, oh0 + dh, b);
         }
-        tma_load_2d(sb, &map_b, bar_full + 8 * s, tap * p.Cin + c0, n0);
+        tma_load_2d(sb, &map_b, bar_full + 8 * s, tap * p.wstride + p.woff + c0, n0);
       }
     }
   } else if (warp == 1) {
@@ -368,7 +369,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int sb = jb % nB;
             mbar_wait(bar_emptyB + 8 * sb, ((jb / nB) & 1) ^ 1);
             mbar_expect_tx(bar_fullB + 8 * sb, b_bytes);
-            tma_load_2d(ring_b + sb * b_bytes, &map_b, bar_fullB + 8 * sb, (kh * 3 + kw) * p.Cin + c0, n0);
+            tma_load_2d(ring_b + sb * b_bytes, &map_b, bar_fullB + 8 * sb, (kh * 3 + kw) * p.wstride + p.woff + c0, n0);
           }
         }
       }
@@ -492,7 +493,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
           const uint32_t sa = base + s * stage_bytes, sb = sa + TC_A_BYTES;
           mbar_expect_tx(bar_full + 8 * s, tx);
           tma_load_2d(sa, &map_a, bar_full + 8 * s, it * TC_BK, m0);
-          tma_load_2d(sb, &map_b, bar_full + 8 * s, it * TC_BK, n0);
+          tma_load_2d(sb, &map_b, bar_full + 8 * s, p.woff + it * TC_BK, n0);
         }
       }
     }
@@ -598,6 +599,8 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
   p.KH = d->KH; p.KW = d->KW; p.pad = d->pad; p.transposed = d->transposed;
   p.Ho = d->Ho; p.Wo = d->Wo; p.P = P;
   p.Cin = d->Cin; p.Cout = d->Cout;
+  p.wstride = d->w_tap_stride ? d->w_tap_stride : d->Cin;
+  p.woff = d->w_koff;
   p.kchunks = (d->Cin + TC_BK - 1) / TC_BK;
   p.ldy = d->ldy; p.out_f32 = d->out_dtype == CRD_F32; p.act = d->act; p.accumulate = d->accumulate;
   // spatial patch: 16 wide unless the image is narrower
@@ -619,7 +622,7 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
     rc = make_map(&map_a, x, 4, dims, str, box);
   }
   if (rc) return rc;
-  const int Ktot = d->KH * d->KW * d->Cin;
+  const int Ktot = d->KH * d->KW * p.wstride;          // weight row length
   cudaStream_t s = (cudaStream_t)stream;
   static int use_halo = -1;
   if (use_halo < 0) {
@@ -950,7 +953,9 @@ extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const vo
   const int gy = p.flat ? (p.kchunks + 2) / 3 : p.kchunks * p.KH;
   const int gz = (d->Cout + 127) / 128;
   // split the pixel tiles so that ~2 waves of CTAs cover the 148 SMs; each split handles >= 4 tiles
-  long long want = (148LL * 2 + (long long)gy * gz - 1) / ((long long)gy * gz);
+  static int wg_target = 0;
+  if (!wg_target) { const char* e = getenv("CAMRADEPTH_WG_CTAS"); wg_target = e ? atoi(e) : 296; if (wg_target < 1) wg_target = 296; }
+  long long want = ((long long)wg_target + (long long)gy * gz - 1) / ((long long)gy * gz);
   long long maxs = (p.total_tiles + 7) / 8;
   long long splits = want < 1 ? 1 : (want > maxs ? maxs : want);
   if (splits < 1) splits = 1;

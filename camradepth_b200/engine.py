@@ -507,14 +507,67 @@ class Engine:
         recs.append(self.convlayer_fwd(cat, f"{prefix}.conv.layers.2", dest, post, save))
         return dict(cat=cat, recs=recs, cs=cs, cxp=cxp) if save else None
 
+    DY_OFF = (0, 96, 160, 288)      # channel offsets of the three layers' dy inside the stacked dy buffer
+
+    def _stacked_dgrad_w(self, prefix):
+        """[ct][9][288] bf16: row c = concat-buffer channel, column (tap, k) = weight of the layer whose output
+        gradient sits at channel k of the stacked dy buffer (zero where a layer does not read channel c)."""
+        names = [f"{prefix}.conv.layers.{li}.model.0.weight" for li in range(3)]
+        ps = [self.P[n] for n in names]
+        key = ("stack", prefix)
+        ver = tuple((p._version, p.data_ptr()) for p in ps) + (WEIGHT_EPOCH[0], self._grad_epoch)
+        ent = self._packs.get(key)
+        if ent is not None and ent[1] == ver:
+            return ent[0]
+        ct = self.L[names[2]]["cin_p"]
+        ktot = self.DY_OFF[3]
+        dst = ent[0] if ent is not None and ent[0].device == self.device else \
+            torch.zeros(ct, 9 * ktot, dtype=self.tdtype, device=self.device)
+        flat = dst.view(-1)
+        for li, n in enumerate(names):
+            L = self.L[n]
+            ops.weight_pack(ps[li].detach(), flat[self.DY_OFF[li]:], self._cmap(n), L["cout"], L["cin"], 9,
+                            L["cin_p"], ktot, 1)
+        self._packs[key] = (dst, ver)
+        return dst
+
     def dec_bwd(self, prefix, rec, ddest, dsrc, src_accumulate):
         """Returns the grad of the concat buffer (callers slice the skip part out of it)."""
         cat, recs, cs, cxp = rec["cat"], rec["recs"], rec["cs"], rec["cxp"]
         ct = cxp + 160
         dcat = self._empty(*cat.shape)
-        self.convlayer_bwd(f"{prefix}.conv.layers.2", recs[2], ddest, dcat, False)
-        self.convlayer_bwd(f"{prefix}.conv.layers.1", recs[1], dcat[..., cxp + 96:ct], dcat[..., :cxp + 96], True)
-        self.convlayer_bwd(f"{prefix}.conv.layers.0", recs[0], dcat[..., cxp:cxp + 96], dcat[..., :cxp], True)
+        if not (self.use_tc and self.tdtype == torch.bfloat16):
+            self.convlayer_bwd(f"{prefix}.conv.layers.2", recs[2], ddest, dcat, False)
+            self.convlayer_bwd(f"{prefix}.conv.layers.1", recs[1], dcat[..., cxp + 96:ct], dcat[..., :cxp + 96], True)
+            self.convlayer_bwd(f"{prefix}.conv.layers.0", recs[0], dcat[..., cxp:cxp + 96], dcat[..., :cxp], True)
+        else:
+            # Data gradients by OUTPUT-channel block with concatenated K: the block of concat channels that only
+            # layer 2 reads gets one GEMM over dy2, the block layers 1+2 read gets one GEMM over [dy1|dy2], the block
+            # all three read one GEMM over [dy0|dy1|dy2].  Same MACs as three per-layer dgrads, but every output
+            # element is written once (no read-modify-write epilogue) and K is 2-3x longer.
+            B_, H_, W_, _ = cat.shape
+            off = self.DY_OFF
+            dycat = self._empty(B_, H_, W_, off[3])
+            wb = self._stacked_dgrad_w(prefix)
+            row_lo = (0, cxp, cxp + 96)              # first concat channel of the block finished after layer li
+            row_hi = (cxp, cxp + 96, ct)
+            ddests = (dcat[..., cxp:cxp + 96], dcat[..., cxp + 96:ct], ddest)
+            for li in (2, 1, 0):
+                name = f"{prefix}.conv.layers.{li}"
+                r = recs[li]
+                L = self.L[name + ".model.0.weight"]
+                dy = dycat[..., off[li]:off[li + 1]]
+                self.gn_bwd(ddests[li], r["y"], r["ab"], r["mr"], name + ".model.1", L["cout"] // self.cfg.gn_div,
+                            ops.ACT_GELU, r["post"], None, dy, False)
+                self.conv_wgrad(r["x"], dy, name + ".model.0.weight")
+                a = dycat[..., off[li]:]
+                out = dcat[..., row_lo[li]:row_hi[li]]
+                d = ops.make_desc(a, out, a.shape[-1], row_hi[li] - row_lo[li], 3, 3, 1, 1, transposed=1,
+                                  w_tap_stride=off[3], w_koff=off[li])
+                ev = self._timed("dgrad", name + ".model.0.weight")
+                ops.conv_fwd(d, a, wb[row_lo[li]:row_hi[li]], None, out, use_tc=True)
+                if ev is not None:
+                    ev.record()
         if dsrc is not None:
             ops.bicubic2x_bwd(dcat[..., :cs], dsrc, src_accumulate)
         return dcat

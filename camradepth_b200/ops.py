@@ -67,7 +67,7 @@ def nhwc_to_nchw(src, dst):
 
 # ------------------------------------------------------------------ conv
 def make_desc(x, y, Cin, Cout, KH, KW, stride, pad, transposed=0, act=0, accumulate=0, out_nchw=0,
-              out_dtype=None, in_dtype=None):
+              out_dtype=None, in_dtype=None, w_tap_stride=0, w_koff=0):
     d = ConvDesc()
     d.B, d.H, d.W = x.shape[0], x.shape[1], x.shape[2]
     d.Cin, d.ldx = Cin, _ld(x)
@@ -83,6 +83,7 @@ def make_desc(x, y, Cin, Cout, KH, KW, stride, pad, transposed=0, act=0, accumul
     d.in_dtype = dcode(x) if in_dtype is None else in_dtype
     d.out_dtype = dcode(y) if out_dtype is None else out_dtype
     d.act, d.accumulate, d.out_nchw = act, accumulate, out_nchw
+    d.w_tap_stride, d.w_koff = w_tap_stride, w_koff
     return d
 
 

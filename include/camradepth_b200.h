@@ -68,6 +68,8 @@ typedef struct {
   int act;              /* CRD_ACT_NONE or CRD_ACT_SIGMOID applied after bias */
   int accumulate;       /* y += result */
   int out_nchw;         /* write y as NCHW (B,Cout,Ho,Wo); ldy ignored */
+  int w_tap_stride;     /* tensor-core path only: elements between taps in a weight row (0 = Cin) ...       */
+  int w_koff;           /* ... and first column used inside each tap: w[n][tap*w_tap_stride + w_koff + c]   */
 } crd_conv_desc;
 
 /* generic CUDA-core path (any shape; the only path in fp32-exact mode) */
