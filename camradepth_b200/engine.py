@@ -35,6 +35,12 @@ def r8(c):
     return (c + 7) // 8 * 8
 
 
+def r64(c):
+    """Pixel stride (in channels) of the wide decoder buffers: a multiple of 64 bf16 = 128 bytes, so every
+    64-channel TMA row of a tap/chunk starts on a 128-byte line (an unaligned row costs two L2 requests)."""
+    return (c + 63) // 64 * 64 if os.environ.get("CAMRADEPTH_PAD128", "1") == "1" else c
+
+
 class ZeroArena:
     """Bump allocator over one zero-filled fp32 buffer (one memset per pass instead of hundreds)."""
 
@@ -496,7 +502,7 @@ class Engine:
         cxp = r8(cx)
         B, h, w, cs = src.shape
         ct = cxp + 160
-        cat = self._empty(B, 2 * h, 2 * w, ct)
+        cat = self._empty(B, 2 * h, 2 * w, r64(ct))[..., :ct]
         ops.bicubic2x_fwd(src, cat[..., :cs])
         if skip_fn is not None:
             skip_fn(cat)
@@ -535,7 +541,7 @@ class Engine:
         """Returns the grad of the concat buffer (callers slice the skip part out of it)."""
         cat, recs, cs, cxp = rec["cat"], rec["recs"], rec["cs"], rec["cxp"]
         ct = cxp + 160
-        dcat = self._empty(*cat.shape)
+        dcat = self._empty(cat.shape[0], cat.shape[1], cat.shape[2], r64(ct))[..., :ct]
         if not (self.use_tc and self.tdtype == torch.bfloat16):
             self.convlayer_bwd(f"{prefix}.conv.layers.2", recs[2], ddest, dcat, False)
             self.convlayer_bwd(f"{prefix}.conv.layers.1", recs[1], dcat[..., cxp + 96:ct], dcat[..., :cxp + 96], True)
@@ -547,7 +553,7 @@ class Engine:
             # element is written once (no read-modify-write epilogue) and K is 2-3x longer.
             B_, H_, W_, _ = cat.shape
             off = self.DY_OFF
-            dycat = self._empty(B_, H_, W_, off[3])
+            dycat = self._empty(B_, H_, W_, r64(off[3]))[..., :off[3]]
             wb = self._stacked_dgrad_w(prefix)
             row_lo = (0, cxp, cxp + 96)              # first concat channel of the block finished after layer li
             row_hi = (cxp, cxp + 96, ct)
