@@ -747,6 +747,7 @@ struct WgParams {
   int KH, KW, pad;
   int Cin, Cout, kchunks;
   int mblocks;              // 64-channel blocks of dY in this launch (1 or 2)
+  int halo;                 // 3x3: one X box with TH+2 rows per (chunk, kw); the kh taps are its 2-KiB row offsets
   long long Ktot;           // row stride of dw
 };
 
@@ -767,8 +768,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                 const WgParams p, float* __restrict__ dw) {
   constexpr int WG_BLK_BYTES = WG_PIX * 64 * 2;
-  constexpr int WG_STAGE_BYTES = 5 * WG_BLK_BYTES;                // 2 dY blocks + 3 X blocks
-  constexpr int WG_STAGES = (200 * 1024) / WG_STAGE_BYTES;
+  constexpr int WG_HALO_X_BYTES = (WG_PIX / 16 + 2) * 16 * 128;   // X box with two halo rows (TW = 16)
+  const int WG_STAGE_BYTES = p.halo ? 2 * WG_BLK_BYTES + WG_HALO_X_BYTES : 5 * WG_BLK_BYTES;
+  const int WG_STAGES = min(WG_MAX_STAGES, (200 * 1024) / WG_STAGE_BYTES);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + WG_STAGES * WG_STAGE_BYTES;
@@ -778,7 +780,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // work column: (chunk, kh) for KxK; a group of up to 3 chunks for 1x1
-  int c0, kh = 0, nblk;
+  int c0, kh = 0, nblk;       // in halo mode `kh` holds the CTA's kw and the N blocks are the three kh taps
   if (p.KH > 1) {
     const int chunk = blockIdx.y / p.KH;
     kh = blockIdx.y - chunk * p.KH;
@@ -813,7 +815,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   if (ntiles > 0) {
     if (warp == 0) {
       if (lane == 0) {
-        const uint32_t tx = (uint32_t)(mblocks + nblk) * WG_BLK_BYTES;
+        const uint32_t tx = p.halo ? (uint32_t)mblocks * WG_BLK_BYTES + WG_HALO_X_BYTES
+                                   : (uint32_t)(mblocks + nblk) * WG_BLK_BYTES;
         // tile coordinates advance incrementally (no 64-bit divisions on the producer's critical path)
         int tw = 0, th = 0, bb = 0, m0 = 0;
         if (p.flat) {
@@ -839,8 +842,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             const int oh0 = th * p.TH, ow0 = tw * p.TW;
             for (int j = 0; j < mblocks; j++)
               tma_load_4d(sa + j * WG_BLK_BYTES, &map_dy, bar, co0 + 64 * j, ow0, oh0, bb);
-            for (int j = 0; j < nblk; j++)
-              tma_load_4d(sb + j * WG_BLK_BYTES, &map_x, bar, c0, ow0 + j - p.pad, oh0 + kh - p.pad, bb);
+            if (p.halo) {
+              tma_load_4d(sb, &map_x, bar, c0, ow0 + kh - p.pad, oh0 - p.pad, bb);       // kh == this CTA's kw
+            } else {
+              for (int j = 0; j < nblk; j++)
+                tma_load_4d(sb + j * WG_BLK_BYTES, &map_x, bar, c0, ow0 + j - p.pad, oh0 + kh - p.pad, bb);
+            }
             if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++bb; } }
           }
         }
@@ -858,7 +865,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
 #pragma unroll
           for (int k = 0; k < WG_PIX / 16; k++) {       // 16 pixels (two 8-row groups = 2048 B) per MMA
             const uint64_t ad = umma_desc_mnmajor_sw128(sa + k * 2048, WG_BLK_BYTES);
-            const uint64_t bd = umma_desc_mnmajor_sw128(sb + k * 2048, WG_BLK_BYTES);
+            // halo mode: N block j = tap kh=j = the same box shifted by j image rows (16 px * 128 B = 2 KiB)
+            const uint64_t bd = umma_desc_mnmajor_sw128(sb + k * 2048, p.halo ? 2048u : (uint32_t)WG_BLK_BYTES);
             umma_bf16_ss(tmem_base, ad, bd, idesc, (it | k) != 0);
           }
           umma_commit(bar_empty + 8 * s);
@@ -878,7 +886,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         const int j = c >> 6, col = c & 63;
         long long kbase;
         int cc;
-        if (p.KH > 1) { cc = c0 + col; kbase = (long long)(kh * p.KW + j) * p.Cin + cc; }
+        if (p.KH > 1) {
+          cc = c0 + col;
+          kbase = (long long)(p.halo ? (j * p.KW + kh) : (kh * p.KW + j)) * p.Cin + cc;
+        }
         else { cc = c0 + 64 * j + col; kbase = cc; }
         float* dst = dw + (long long)co * p.Ktot + kbase;
 #pragma unroll
@@ -923,6 +934,9 @@ extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const vo
   p.kchunks = (d->Cin + 63) / 64;
   p.mblocks = d->Cout > 64 ? 2 : 1;
   p.Ktot = (long long)d->KH * d->KW * d->Cin;
+  static int wg_halo = -1;
+  if (wg_halo < 0) { const char* e = getenv("CAMRADEPTH_WG_HALO"); wg_halo = (e && e[0] == '0') ? 0 : 1; }
+  p.halo = (wg_halo && d->KH == 3 && d->W >= 16) ? 1 : 0;
   p.TW = d->W >= 16 ? 16 : (d->W >= 8 ? 8 : 4);
   p.TH = WG_PIX / p.TW;
   p.tiles_w = (d->W + p.TW - 1) / p.TW;
@@ -947,7 +961,8 @@ extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const vo
     if (rc) return rc;
     cuuint64_t dims2[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
     cuuint64_t str2[3] = {(cuuint64_t)d->ldx * 2, (cuuint64_t)d->W * d->ldx * 2, (cuuint64_t)d->H * d->W * d->ldx * 2};
-    rc = make_map(&map_x, x, 4, dims2, str2, box);
+    cuuint32_t boxx[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)(p.TH + (p.halo ? 2 : 0)), 1};
+    rc = make_map(&map_x, x, 4, dims2, str2, boxx);
   }
   if (rc) return rc;
   const int gy = p.flat ? (p.kchunks + 2) / 3 : p.kchunks * p.KH;
