@@ -920,8 +920,8 @@ extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const vo
   static int WG_PIX = 0;
   if (!WG_PIX) {
     const char* e = getenv("CAMRADEPTH_WG_PIX");
-    WG_PIX = e ? atoi(e) : 64;
-    if (WG_PIX != 32 && WG_PIX != 64 && WG_PIX != 128) WG_PIX = 64;
+    WG_PIX = e ? atoi(e) : 128;
+    if (WG_PIX != 32 && WG_PIX != 64 && WG_PIX != 128) WG_PIX = 128;
     cudaError_t e1 = cudaFuncSetAttribute(wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
     cudaError_t e2 = cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
     cudaError_t e3 = cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
