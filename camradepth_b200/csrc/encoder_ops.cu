@@ -162,6 +162,81 @@ __global__ void dwconv_bwd_weight_kernel(const T* __restrict__ dy, const T* __re
   }
 }
 
+// Fused depthwise backward: one pass over dy produces BOTH the input gradient and the weight/bias gradients.
+// With q the input pixel, dxn[q] = sum_t w[t] dy[q - t] and dw[t] += dy[q - t] * xn[q] use the same nine dy
+// neighbours, so the separate weight-gradient kernel's nine extra loads per pixel disappear.
+template <typename T>
+__global__ void __launch_bounds__(256, 1) dwconv_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                  const float* __restrict__ ab,
+                                                                  const float* __restrict__ w, T* __restrict__ dxn,
+                                                                  float* dw, float* db, int B, int H, int W, int C,
+                                                                  long long ppb) {
+  extern __shared__ float red[];
+  const int cv = threadIdx.x, ry = threadIdx.y, rows = blockDim.y, cvec = blockDim.x;
+  const int c = cv * 8, b = blockIdx.y;
+  const long long N = (long long)H * W;
+  long long p0 = (long long)blockIdx.x * ppb, p1 = p0 + ppb;
+  if (p1 > N) p1 = N;
+  float wt[9][8], a[8], sh[8], acc[10][8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    a[j] = ab[((long long)b * C + c + j) * 2];
+    sh[j] = ab[((long long)b * C + c + j) * 2 + 1];
+#pragma unroll
+    for (int t = 0; t < 9; t++) wt[t][j] = w[(c + j) * 9 + t];
+  }
+#pragma unroll
+  for (int q = 0; q < 10; q++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[q][j] = 0.f;
+  const T* gb = dy + (long long)b * N * C + c;
+  const T* xb = x + (long long)b * N * C + c;
+  T* ob = dxn + (long long)b * N * C + c;
+  for (int p = (int)p0 + ry; p < (int)p1; p += rows) {
+    const int hh = p / W, ww = p - hh * W;
+    typename Raw8<T>::type raw[9];
+    bool ok[9];
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+      const int h2 = hh - (t / 3 - 1), w2 = ww - (t % 3 - 1);   // output pixel that read input p with tap t
+      ok[t] = (h2 >= 0) & (h2 < H) & (w2 >= 0) & (w2 < W);
+      const int hc = min(max(h2, 0), H - 1), wc = min(max(w2, 0), W - 1);
+      raw[t] = ldg16(gb + (size_t)(hc * W + wc) * C);
+    }
+    float xv[8], o[8];
+    load8(xb + (size_t)p * C, xv);
+#pragma unroll
+    for (int j = 0; j < 8; j++) { xv[j] = fmaf(a[j], xv[j], sh[j]); o[j] = 0.f; }
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+      float g[8];
+      unpack8(raw[t], g);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float gj = ok[t] ? g[j] : 0.f;
+        o[j] = fmaf(wt[t][j], gj, o[j]);
+        acc[t][j] = fmaf(gj, xv[j], acc[t][j]);
+        if (t == 4) acc[9][j] += gj;                           // centre tap: dy at this pixel -> bias gradient
+      }
+    }
+    store8(ob + (size_t)p * C, o);
+  }
+#pragma unroll
+  for (int q = 0; q < 10; q++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) red[(ry * cvec + cv) * 8 + j] = acc[q][j];
+    __syncthreads();
+    const int t = ry * cvec + cv, nt = rows * cvec;
+    for (int cc = t; cc < C; cc += nt) {
+      float s = 0.f;
+      for (int r = 0; r < rows; r++) s += red[r * cvec * 8 + cc];
+      if (q < 9) atomicAdd(dw + cc * 9 + q, s);
+      else if (db) atomicAdd(db + cc, s);
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------ attention score
 // block: 64 tokens of one sample; loop heads; per head stage q[64][hd] and key chunks k[64][hd] in smem.
 constexpr int ATN = 64, AMK = 64;
@@ -430,6 +505,17 @@ extern "C" int crd_dwconv3x3_bwd_weight(const void* dy, int dtype, const void* x
   return 0;
 }
 
+extern "C" int crd_dwconv3x3_bwd(const void* dy, int dtype, const void* x, const float* ab, const float* w, void* dxn,
+                                 float* dw, float* db, int B, int H, int W, int C, crd_stream_t stream) {
+  CRD_REQUIRE(C % 8 == 0 && C / 8 <= 256);
+  if (B == 0 || H * W == 0) return 0;
+  ReduceLaunch r = plan_reduce(B, (long long)H * W, C);
+  const size_t smem = (size_t)r.block.x * r.block.y * 8 * sizeof(float);
+  CRD_DISPATCH_1(dtype, T, dwconv_bwd_fused_kernel<T><<<r.grid, r.block, smem, (cudaStream_t)stream>>>(
+                               (const T*)dy, (const T*)x, ab, w, (T*)dxn, dw, db, B, H, W, C, r.ppb));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
 extern "C" int crd_attn_qkmax_fwd(const void* q, const void* k, int dtype, float* s, unsigned short* idx, int B,
                                   int N, int M, int C, int heads, float scale, crd_stream_t stream) {
   CRD_REQUIRE(heads > 0 && C % heads == 0 && M >= 1 && M <= 65535);   // idx is uint16

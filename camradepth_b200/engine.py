@@ -425,10 +425,9 @@ class Engine:
         self.gn_bwd(dh3, rec["h2"], rec["ab_m2"], rec["mr_m2"], p + ".mlp1.norm2", G, ops.ACT_GELU, None, None, dh2,
                     False)
         del dh3
-        ops.dwconv_bwd_weight(dh2, rec["h1"], rec["ab_m1"], self.pg[p + ".mlp1.dwconv.dwconv.weight"],
-                              self.pg[p + ".mlp1.dwconv.dwconv.bias"])
         dh1n = self._empty(B, H, W, rC)
-        ops.dwconv_bwd_input(dh2, self.P[p + ".mlp1.dwconv.dwconv.weight"].detach(), dh1n)
+        ops.dwconv_bwd(dh2, rec["h1"], rec["ab_m1"], self.P[p + ".mlp1.dwconv.dwconv.weight"].detach(), dh1n,
+                       self.pg[p + ".mlp1.dwconv.dwconv.weight"], self.pg[p + ".mlp1.dwconv.dwconv.bias"])
         dh1 = dh2   # reuse
         self.gn_bwd(dh1n, rec["h1"], rec["ab_m1"], rec["mr_m1"], p + ".mlp1.norm1", rC // cfg.gn_div, ops.ACT_NONE,
                     None, None, dh1, False)

@@ -190,6 +190,12 @@ def dwconv_bwd_weight(dy, x, ab, dw, db):
     K.crd_dwconv3x3_bwd_weight(P(dy), dcode(dy), P(x), P(ab), P(dw), P(db), B, H, W, C, stream())
 
 
+def dwconv_bwd(dy, x, ab, w, dxn, dw, db):
+    B, H, W, C = dy.shape
+    assert dy.is_contiguous() and x.is_contiguous() and dxn.is_contiguous()
+    K.crd_dwconv3x3_bwd(P(dy), dcode(dy), P(x), P(ab), P(w), P(dxn), P(dw), P(db), B, H, W, C, stream())
+
+
 def attn_qkmax_fwd(q, k, s, idx, heads, scale):
     B, N, C = q.shape
     M = k.shape[1]

@@ -136,6 +136,9 @@ CRD_API int crd_dwconv3x3_fwd(const void* x, int dtype, const float* ab, const f
                       void* y, int B, int H, int W, int C, crd_stream_t stream);
 CRD_API int crd_dwconv3x3_bwd_input(const void* dy, int dtype, const float* w, void* dxn, int B, int H, int W, int C,
                             crd_stream_t stream);
+/* fused backward: dxn (input gradient) and dw/db (accumulated) from ONE pass over dy */
+CRD_API int crd_dwconv3x3_bwd(const void* dy, int dtype, const void* x, const float* ab, const float* w, void* dxn,
+                      float* dw, float* db, int B, int H, int W, int C, crd_stream_t stream);
 CRD_API int crd_dwconv3x3_bwd_weight(const void* dy, int dtype, const void* x, const float* ab, float* dw, float* db,
                              int B, int H, int W, int C, crd_stream_t stream);
 /* Attention_MaxPool (simplified_attention.py:90-109), algebraically reduced:

@@ -222,6 +222,12 @@ def test_dwconv(dtype):
     dw, db = torch.zeros(C, 9, device=d), torch.zeros(C, device=d)
     ops.dwconv_bwd_weight(dy, xb, ab, dw, db)
     assert rel(dw, wr.grad.view(C, 9)) < 1e-3 and rel(db, rnd(gy, dtype).sum((0, 2, 3))) < 1e-4
+    # fused backward (one pass over dy)
+    dxn2 = torch.empty(B, H, W, C, dtype=dtype, device=d)
+    dw2, db2 = torch.zeros(C, 9, device=d), torch.zeros(C, device=d)
+    ops.dwconv_bwd(dy, xb, ab, w, dxn2, dw2, db2)
+    assert rel(nchw(dxn2), xn.grad) < TOL[dtype]
+    assert rel(dw2, wr.grad.view(C, 9)) < 1e-3 and rel(db2, rnd(gy, dtype).sum((0, 2, 3))) < 1e-4
 
 
 @pytest.mark.parametrize("dtype", DT)
