@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--quick", action="store_true", help="resident timing only (for ncu launch lists): no e2e / roofline passes")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
@@ -286,6 +287,13 @@ def main():
     sampler.stop_flag = True
     launches = launches_per_step * a.steps
     ms = e0.elapsed_time(e1)
+    if a.quick:
+        if rank == 0:
+            print(json.dumps({"metric": "train samples/s", "value": world * B * a.steps / (ms / 1e3),
+                              "ms_per_step": ms / a.steps, "quick": True}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # ---- end-to-end timing (host buffers)
     for _ in range(2):
         run_e2e()
