@@ -64,7 +64,10 @@ inline ReduceLaunch plan_reduce(int B, long long N, int C) {
   ReduceLaunch r;
   int cvec = C / 8;
   int rows = 256 / cvec; if (rows < 1) rows = 1; if (rows > 32) rows = 32;
-  long long blocks_per_b = (148LL * 6 + B - 1) / B;
+  // total blocks just UNDER 148 * 12 = a whole number of waves for 2, 3, 4 or 6 resident blocks per SM
+  // (896 blocks at 4 blocks/SM was 1.51 waves: a quarter of the time spent in a half-empty tail)
+  long long blocks_per_b = (148LL * 12) / B;
+  if (blocks_per_b < 1) blocks_per_b = 1;
   long long min_ppb = rows * 4;
   long long ppb = (N + blocks_per_b - 1) / blocks_per_b;
   if (ppb < min_ppb) ppb = min_ppb;
@@ -81,7 +84,8 @@ inline ReduceLaunch plan_stream(int B, long long N, int C) {
   ReduceLaunch r;
   int cvec = C / 8;
   int rows = 256 / cvec; if (rows < 1) rows = 1; if (rows > 32) rows = 32;
-  long long blocks_per_b = (148LL * 16 + B - 1) / B;
+  long long blocks_per_b = (148LL * 12) / B;       // whole waves for 2, 3, 4 or 6 resident blocks per SM
+  if (blocks_per_b < 1) blocks_per_b = 1;
   long long min_ppb = rows * 8;
   long long ppb = (N + blocks_per_b - 1) / blocks_per_b;
   if (ppb < min_ppb) ppb = min_ppb;
