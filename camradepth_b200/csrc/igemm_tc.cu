@@ -563,6 +563,25 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+// cudaFuncSetAttribute is per device: remember which devices have been prepared (a process may drive several GPUs)
+template <typename K>
+int ensure_smem_attr(K kernel, int bytes, unsigned long long& done_mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -12;
+  if (dev < 64 && (done_mask >> dev) & 1ull) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 64) done_mask |= 1ull << dev;
+  return 0;
+}
+
+int sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  return n;
+}
+
 int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
              const cuuint32_t* box) {
   EncodeTiledFn enc = get_encode();
@@ -587,13 +606,8 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
   CRD_REQUIRE(d->KH == d->KW && 2 * d->pad == d->KH - 1);
   const long long P = (long long)d->B * d->H * d->W;
   if (P == 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TC_SMEM_BUDGET + 2048);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static unsigned long long attr_v1 = 0;
+  if (int e = ensure_smem_attr(conv_tc_kernel, TC_SMEM_BUDGET + 2048, attr_v1)) return e;
   TcParams p;
   p.flat = (d->KH == 1);
   p.KH = d->KH; p.KW = d->KW; p.pad = d->pad; p.transposed = d->transposed;
@@ -633,19 +647,9 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
   // convs 7.9 -> 4.6 ms, depth-head convs 0.8 -> 0.5 ms); the wide-N data gradients of the dense blocks
   // (136..296 output channels, K = 9 * 64..128) stay on the plain kernel (8.6 vs 9.7 ms).
   if (use_halo && d->KH == 3 && d->H % 16 == 0 && d->W >= 16 && d->Cout <= 128 && d->Cin >= 32) {
-    static int num_sms = 0;
-    if (!num_sms) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-      if (num_sms <= 0) num_sms = 148;
-    }
-    static bool halo_attr = false;
-    if (!halo_attr) {
-      cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) return (int)e;
-      halo_attr = true;
-    }
+    const int num_sms = sm_count();
+    static unsigned long long attr_halo = 0;
+    if (int e = ensure_smem_attr(conv_tc_halo_kernel, 227 * 1024, attr_halo)) return e;
     const int ntile = (d->Cout + 127) / 128;          // accumulators are 128 TMEM columns each, double buffered
     p.bn = ((d->Cout + ntile - 1) / ntile + 15) / 16 * 16;
     p.tmem_cols = 512;
@@ -677,18 +681,9 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
   // measured slower than two one-tile CTAs per SM (8 epilogue warps instead of 4): opt-in only
   if (use_pgemm < 0) { const char* e = getenv("CAMRADEPTH_TC_PGEMM"); use_pgemm = (e && e[0] == '1') ? 1 : 0; }
   if (use_pgemm && p.flat) {
-    static bool pg_attr = false;
-    static int pg_sms = 148;
-    if (!pg_attr) {
-      cudaError_t e = cudaFuncSetAttribute(gemm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           227 * 1024);
-      if (e != cudaSuccess) return (int)e;
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&pg_sms, cudaDevAttrMultiProcessorCount, dev);
-      if (pg_sms <= 0) pg_sms = 148;
-      pg_attr = true;
-    }
+    static unsigned long long attr_pg = 0;
+    if (int e = ensure_smem_attr(gemm_tc_persistent_kernel, 227 * 1024, attr_pg)) return e;
+    const int pg_sms = sm_count();
     const int ntile = (d->Cout + 255) / 256;
     p.bn = ((d->Cout + ntile - 1) / ntile + 15) / 16 * 16;
     p.tmem_cols = p.bn <= 128 ? 256 : 512;               // two accumulator buffers
@@ -922,10 +917,15 @@ extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const vo
     const char* e = getenv("CAMRADEPTH_WG_PIX");
     WG_PIX = e ? atoi(e) : 128;
     if (WG_PIX != 32 && WG_PIX != 64 && WG_PIX != 128) WG_PIX = 128;
-    cudaError_t e1 = cudaFuncSetAttribute(wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
-    cudaError_t e2 = cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
-    cudaError_t e3 = cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { WG_PIX = 0; return (int)(e1 ? e1 : (e2 ? e2 : e3)); }
+  }
+  static unsigned long long attr_wg = 0;
+  {
+    unsigned long long m1 = attr_wg, m2 = attr_wg, m3 = attr_wg;
+    int e1 = ensure_smem_attr(wgrad_tc_kernel<32>, WG_SMEM, m1);
+    int e2 = ensure_smem_attr(wgrad_tc_kernel<64>, WG_SMEM, m2);
+    int e3 = ensure_smem_attr(wgrad_tc_kernel<128>, WG_SMEM, m3);
+    if (e1 || e2 || e3) return e1 ? e1 : (e2 ? e2 : e3);
+    attr_wg = m1 & m2 & m3;
   }
   WgParams p;
   p.flat = (d->KH == 1);

@@ -192,3 +192,30 @@ def test_properties_full_batch():
     assert full.shape == (4, 1, 192, 416)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 7, 192, 400, device="cuda"))          # reference also fails on 400-wide input (F2)
+
+
+def test_edge_cases_native_resolution_and_empty_mask():
+    """Reference-native 416x800 input (args.py:19), odd batch, and the loss on an empty valid mask (NaN, like the
+    reference's mean over an empty selection, loss_funcs.py:83-91)."""
+    import camradepth_b200 as C
+    from camradepth_b200.synthetic import make_batch
+    C.set_model("base")
+    torch.manual_seed(0)
+    m = C.CamRaDepth(precision="bf16").cuda().eval()
+    b = {k: v.cuda() for k, v in make_batch(3, 416, 800, seed=6).items()}
+    pred = m(b["image"])
+    assert pred["depth"]["final_depth"].shape == (3, 1, 416, 800)
+    assert pred["depth"]["intermediate_depths"][2].shape == (3, 1, 104, 200)
+    assert pred["depth"]["intermediate_depths"][3].shape == (3, 1, 208, 400)
+    loss = C.MaskedSmoothL1Loss()(pred["depth"]["final_depth"], b["gt_final"])
+    loss.backward()
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(loss))
+    for n, p in m.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), n
+    empty = C.MaskedSmoothL1Loss()(pred["depth"]["final_depth"].detach(), torch.zeros_like(b["gt_final"]))
+    assert bool(torch.isnan(empty))
+    # eval-mode forward of one sample is independent of its batch mates at this size too
+    with torch.no_grad():
+        one = m(b["image"][1:2])["depth"]["final_depth"]
+    assert relerr(pred["depth"]["final_depth"][1:2], one) < 5e-3
