@@ -5,6 +5,7 @@
 // (block, channel).
 #include "common.cuh"
 #include "chan_reduce.cuh"
+#include "gn_stream_tma.cuh"
 #include "../../include/camradepth_b200.h"
 
 namespace {
@@ -302,6 +303,15 @@ extern "C" int crd_chan_stats(const void* x, int dtype, float* sums, int B, long
                               crd_stream_t stream) {
   CRD_REQUIRE(C % 8 == 0 && C / 8 <= 256 && ld % 8 == 0);
   if (B == 0 || N == 0) return 0;
+  if (dtype == CRD_BF16 && st_eligible(B, N, C, x, ld, nullptr, 0)) {
+    StLaunch L = st_plan(B, N, C);
+    L.p.red = sums;
+    CUtensorMap m0;
+    if (int e = st_map(&m0, x, B, N, C, ld, L.p)) return e;
+    if (int e = st_launch<ST_STATS>(L, m0, m0, (cudaStream_t)stream)) return e;
+    CRD_LAUNCH_CHECK();
+    return 0;
+  }
   ReduceLaunch r = plan_reduce(B, N, C);
   CRD_DISPATCH_1(dtype, T, chan_stats_kernel<T><<<r.grid, r.block, r.smem, (cudaStream_t)stream>>>(
                                 (const T*)x, sums, B, N, C, ld, r.ppb));
@@ -326,6 +336,15 @@ extern "C" int crd_affine_act(const void* x, int in_dtype, void* y, int out_dtyp
   CRD_REQUIRE(C / 8 <= 256);
   if ((long long)B * N == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
+  if (in_dtype == CRD_BF16 && out_dtype == CRD_BF16 && st_eligible(B, N, C, x, ldx, y, ldy)) {
+    StLaunch L = st_plan(B, N, C);
+    L.p.ab = ab; L.p.post = post; L.p.act = act; L.p.out = (bf16*)y; L.p.ldo = ldy;
+    CUtensorMap m0;
+    if (int e = st_map(&m0, x, B, N, C, ldx, L.p)) return e;
+    if (int e = st_launch<ST_AFFINE>(L, m0, m0, s)) return e;
+    CRD_LAUNCH_CHECK();
+    return 0;
+  }
   ReduceLaunch r = plan_stream(B, N, C);
   CRD_DISPATCH_1(in_dtype, TI, CRD_DISPATCH_1(out_dtype, TO, affine_act_kernel<TI, TO><<<r.grid, r.block, 0, s>>>(
                                    (const TI*)x, (TO*)y, ab, post, act, B, N, C, ldx, ldy, r.ppb)));
@@ -338,8 +357,19 @@ extern "C" int crd_gnact_bwd_reduce(const void* dy, int dy_dtype, const void* x,
                                     int B, long long N, int C, int lddy, int ldx, crd_stream_t stream) {
   CRD_REQUIRE(C % 8 == 0 && C / 8 <= 256 && lddy % 8 == 0 && ldx % 8 == 0);
   if (B == 0 || N == 0) return 0;
-  ReduceLaunch r = plan_reduce(B, N, C);
   cudaStream_t s = (cudaStream_t)stream;
+  if (dy_dtype == CRD_BF16 && x_dtype == CRD_BF16 && st_eligible(B, N, C, dy, lddy, x, ldx)) {
+    StLaunch L = st_plan(B, N, C);
+    L.p.ab = ab; L.p.post = post; L.p.addbc = addbc; L.p.act = act; L.p.red = pq;
+    L.p.out = (bf16*)dz_out; L.p.ldo = lddy;
+    CUtensorMap m0, m1;
+    if (int e = st_map(&m0, dy, B, N, C, lddy, L.p)) return e;
+    if (int e = st_map(&m1, x, B, N, C, ldx, L.p)) return e;
+    if (int e = st_launch<ST_BWD_REDUCE>(L, m0, m1, s)) return e;
+    CRD_LAUNCH_CHECK();
+    return 0;
+  }
+  ReduceLaunch r = plan_reduce(B, N, C);
   CRD_DISPATCH_1(dy_dtype, TD, CRD_DISPATCH_1(x_dtype, TX, gnact_bwd_reduce_kernel<TD, TX><<<r.grid, r.block, r.smem, s>>>(
                                    (const TD*)dy, (const TX*)x, ab, post, addbc, act, pq, (TD*)dz_out, B, N, C, lddy, ldx, r.ppb)));
   CRD_LAUNCH_CHECK();
@@ -364,6 +394,18 @@ extern "C" int crd_gnact_bwd_apply(const void* dy, int dy_dtype, const void* x, 
   CRD_REQUIRE(C / 8 <= 256);
   if ((long long)B * N == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
+  if (dy_dtype == CRD_BF16 && x_dtype == CRD_BF16 && dx_dtype == CRD_BF16 && !accumulate &&
+      st_eligible(B, N, C, dy, lddy, x, ldx) && ((uintptr_t)dx & 15) == 0) {
+    StLaunch L = st_plan(B, N, C);
+    L.p.ab = ab; L.p.post = post; L.p.addbc = addbc; L.p.act = act; L.p.coef = coef;
+    L.p.out = (bf16*)dx; L.p.ldo = lddx;
+    CUtensorMap m0, m1;
+    if (int e = st_map(&m0, dy, B, N, C, lddy, L.p)) return e;
+    if (int e = st_map(&m1, x, B, N, C, ldx, L.p)) return e;
+    if (int e = st_launch<ST_BWD_APPLY>(L, m0, m1, s)) return e;
+    CRD_LAUNCH_CHECK();
+    return 0;
+  }
   ReduceLaunch r = plan_stream(B, N, C);
   CRD_DISPATCH_1(dy_dtype, TD, CRD_DISPATCH_1(x_dtype, TX, CRD_DISPATCH_1(dx_dtype, TO,
       gnact_bwd_apply_kernel<TD, TX, TO><<<r.grid, r.block, 0, s>>>((const TD*)dy, (const TX*)x, ab, post, addbc, act,
