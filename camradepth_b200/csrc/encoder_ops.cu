@@ -4,6 +4,7 @@
 // output fused with the residual/DropPath add, and their backward passes.
 #include "common.cuh"
 #include "chan_reduce.cuh"
+#include "dwconv_tma.cuh"
 #include "../../include/camradepth_b200.h"
 
 namespace {
@@ -477,6 +478,13 @@ extern "C" int crd_dwconv3x3_fwd(const void* x, int dtype, const float* ab, cons
                                  void* y, int B, int H, int W, int C, crd_stream_t stream) {
   CRD_REQUIRE(C % 8 == 0 && C / 8 <= 256);
   if ((long long)B * H * W == 0) return 0;
+  if (dw_tma_eligible(dtype, B, H, W, C, x, x, y)) {
+    DwParams p = {};
+    p.B = B; p.H = H; p.W = W; p.C = C; p.ab = ab; p.w = w; p.bias = bias; p.out = (bf16*)y;
+    if (int e = dw_tma_launch<false>(x, nullptr, p, (cudaStream_t)stream)) return e;
+    CRD_LAUNCH_CHECK();
+    return 0;
+  }
   ReduceLaunch r = plan_stream(B, (long long)H * W, C);
   CRD_DISPATCH_1(dtype, T, dwconv_fwd_kernel<T><<<r.grid, r.block, 0, (cudaStream_t)stream>>>(
                                (const T*)x, ab, w, bias, (T*)y, B, H, W, C, r.ppb));
@@ -509,6 +517,13 @@ extern "C" int crd_dwconv3x3_bwd(const void* dy, int dtype, const void* x, const
                                  float* dw, float* db, int B, int H, int W, int C, crd_stream_t stream) {
   CRD_REQUIRE(C % 8 == 0 && C / 8 <= 256);
   if (B == 0 || H * W == 0) return 0;
+  if (dw_tma_eligible(dtype, B, H, W, C, dy, x, dxn)) {
+    DwParams p = {};
+    p.B = B; p.H = H; p.W = W; p.C = C; p.ab = ab; p.w = w; p.out = (bf16*)dxn; p.dw = dw; p.db = db;
+    if (int e = dw_tma_launch<true>(dy, x, p, (cudaStream_t)stream)) return e;
+    CRD_LAUNCH_CHECK();
+    return 0;
+  }
   ReduceLaunch r = plan_reduce(B, (long long)H * W, C);
   const size_t smem = (size_t)r.block.x * r.block.y * 8 * sizeof(float);
   CRD_DISPATCH_1(dtype, T, dwconv_bwd_fused_kernel<T><<<r.grid, r.block, smem, (cudaStream_t)stream>>>(

@@ -135,7 +135,11 @@ def test_weight_pack_with_channel_map(dtype):
 
 
 @pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("shape", [(2, 64, 12, 20, 4), (2, 512, 6, 10, 32), (1, 96, 24, 40, 6), (3, 1024, 3, 5, 16)])
+@pytest.mark.parametrize("shape", [(2, 64, 12, 20, 4), (2, 512, 6, 10, 32), (1, 96, 24, 40, 6), (3, 1024, 3, 5, 16),
+                                   # large enough for the TMA-staged bf16 kernels (ragged pixel counts, channel
+                                   # tiles of 128 / 96 / 160 / 64 channels, inputs that are slices of wider buffers)
+                                   (2, 128, 63, 71, 8), (2, 96, 80, 72, 6), (1, 1024, 33, 35, 16), (4, 160, 41, 43, 10),
+                                   (3, 192, 50, 40, 12)])
 @pytest.mark.parametrize("act", [0, 1])
 def test_groupnorm_protocol(shape, act, dtype):
     from camradepth_b200 import ops
@@ -152,6 +156,10 @@ def test_groupnorm_protocol(shape, act, dtype):
     yr = (F.gelu(z) if act else z) * post.view(B, C, 1, 1)
     xb = nhwc(x, dtype)
     N = H * W
+    if B * N * C >= (1 << 20):
+        wide = torch.zeros(B, H, W, C + 24, dtype=dtype, device=d)
+        wide[..., 8:8 + C] = xb
+        xb = wide[..., 8:8 + C]
     sums = torch.zeros(B, C, 2, device=d)
     ops.chan_stats(xb, sums)
     ab = torch.empty(B, C, 2, device=d)
@@ -193,11 +201,15 @@ def test_groupnorm_protocol(shape, act, dtype):
 
 
 @pytest.mark.parametrize("dtype", DT)
-def test_dwconv(dtype):
+@pytest.mark.parametrize("shape", [(2, 160, 9, 14),
+                                   # TMA-staged bf16 path: C % 64 == 0 and >= 2^19 elements; ragged last strip
+                                   # (W = 100), one-strip maps (W = 13), split row ranges, H not a multiple of 6
+                                   (4, 128, 24, 52), (2, 64, 50, 100), (8, 1024, 6, 13), (2, 192, 47, 31)])
+def test_dwconv(shape, dtype):
     from camradepth_b200 import ops
     d = dev()
     torch.manual_seed(2)
-    B, C, H, W = 2, 160, 9, 14
+    B, C, H, W = shape
     x = torch.randn(B, C, H, W, device=d)
     w = torch.randn(C, 1, 3, 3, device=d) * 0.3
     bias = torch.randn(C, device=d)
