@@ -3,6 +3,7 @@
 // segmentation maps, the NCHW<->NHWC boundary converts and weight (un)packing.
 #include "common.cuh"
 #include "chan_reduce.cuh"
+#include "bicubic_tma.cuh"
 #include "../../include/camradepth_b200.h"
 
 namespace {
@@ -431,6 +432,13 @@ extern "C" int crd_bicubic2x_fwd(const void* x, void* y, int dtype, int B, int H
   CRD_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0);
   const long long total = (long long)B * H * W * 4 * (C / 8);
   if (total == 0) return 0;
+  if (bc_tma_eligible(dtype, B, H, W, C, x, ldx, y, ldy)) {
+    BcParams p = {};
+    p.B = B; p.H = H; p.W = W; p.C = C; p.ld_in = ldx; p.ld_out = ldy; p.out = (bf16*)y;
+    if (int e = bc_tma_launch<false>(x, p, (cudaStream_t)stream)) return e;
+    CRD_LAUNCH_CHECK();
+    return 0;
+  }
   CRD_DISPATCH_1(dtype, T, bicubic_fwd_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
                                (const T*)x, (T*)y, B, H, W, C, ldx, ldy));
   CRD_LAUNCH_CHECK();
@@ -441,6 +449,13 @@ extern "C" int crd_bicubic2x_bwd(const void* dy, void* dx, int dtype, int accumu
   CRD_REQUIRE(C % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0);
   const long long total = (long long)B * H * W * (C / 8);
   if (total == 0) return 0;
+  if (bc_tma_eligible(dtype, B, H, W, C, dy, lddy, dx, lddx)) {
+    BcParams p = {};
+    p.B = B; p.H = H; p.W = W; p.C = C; p.ld_in = lddy; p.ld_out = lddx; p.accumulate = accumulate; p.out = (bf16*)dx;
+    if (int e = bc_tma_launch<true>(dy, p, (cudaStream_t)stream)) return e;
+    CRD_LAUNCH_CHECK();
+    return 0;
+  }
   CRD_DISPATCH_1(dtype, T, bicubic_bwd_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
                                (const T*)dy, (T*)dx, accumulate, B, H, W, C, lddy, lddx));
   CRD_LAUNCH_CHECK();

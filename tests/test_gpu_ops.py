@@ -315,7 +315,11 @@ def test_attention_out_and_pv():
 
 
 @pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("shape", [(2, 136, 6, 13), (1, 256, 3, 4), (2, 8, 12, 20)])
+@pytest.mark.parametrize("shape", [(2, 136, 6, 13), (1, 256, 3, 4), (2, 8, 12, 20),
+                                   # TMA-staged bf16 path (>= 2^18 elements): a short third channel tile (136),
+                                   # ragged strips (W = 37), split row ranges, H not a multiple of the box height
+                                   (2, 136, 24, 52), (4, 128, 48, 104), (4, 256, 12, 26), (3, 64, 50, 37),
+                                   (16, 72, 7, 33)])
 def test_bicubic(shape, dtype):
     from camradepth_b200 import ops
     B, C, H, W = shape
@@ -335,6 +339,10 @@ def test_bicubic(shape, dtype):
     dx = torch.ones(B, H, W, C, dtype=dtype, device=d)
     ops.bicubic2x_bwd(dyb[..., :C], dx, True)
     assert rel(nchw(dx) - 1, gx) < 2 * TOL[dtype]
+    dx2 = torch.full((B, H, W, C + 8), 7.0, dtype=dtype, device=d)
+    ops.bicubic2x_bwd(dyb[..., :C], dx2[..., :C], False)
+    assert rel(nchw(dx2[..., :C]), gx) < TOL[dtype]
+    assert float((dx2[..., C:].float() - 7).abs().max()) == 0 and float(ybuf[..., C:].float().abs().max()) == 0
 
 
 @pytest.mark.parametrize("dtype", DT)
