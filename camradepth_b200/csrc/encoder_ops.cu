@@ -535,6 +535,12 @@ extern "C" int crd_attn_qkmax_fwd(const void* q, const void* k, int dtype, float
                                   int N, int M, int C, int heads, float scale, crd_stream_t stream) {
   CRD_REQUIRE(heads > 0 && C % heads == 0 && M >= 1 && M <= 65535);   // idx is uint16
   if (B == 0 || N == 0) return 0;
+  static int qk_tc = -1;
+  if (qk_tc < 0) { const char* e = getenv("CAMRADEPTH_TC_QKMAX"); qk_tc = (e && e[0] == '0') ? 0 : 1; }
+  if (qk_tc && dtype == CRD_BF16) {
+    const int rc = crd_attn_qkmax_fwd_tc(q, k, s, idx, B, N, M, C, heads, scale, stream);
+    if (rc <= 0) return rc;                       // 1 = shape not covered: CUDA-core kernel below
+  }
   const int hd = C / heads;
   const size_t smem = (size_t)(ATN + AMK) * (hd + 1) * sizeof(float);
   dim3 grid(crd_div_up(N, ATN), B);

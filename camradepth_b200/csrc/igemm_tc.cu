@@ -900,3 +900,151 @@ extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const vo
   CRD_LAUNCH_CHECK();
   return 0;
 }
+
+namespace {
+
+// ====================================================================================================
+// Max-pool attention score (simplified_attention.py:96-105): s[b,n] = scale * sum_h max_m q_h[n] . k_h[m]
+// One CTA per 128-token tile; per head one tcgen05 GEMM D[128 tokens][keys] = Q_h K_h^T (K = head_dim, bf16
+// operands, fp32 accumulation in TMEM) whose accumulator never leaves the SM: the four epilogue warps hold one
+// token row per thread (tcgen05.ld 32x32b), so max / argmax over the keys is a register loop without shuffles.
+// Heads are pipelined: two smem stages (TMA) and two TMEM accumulators, so the epilogue of head h overlaps the
+// loads and MMAs of head h+1.  K_h comes through a per-head tensor-map view {hd, heads, M, B} whose
+// out-of-bounds fill zeroes the channels between hd and the next multiple of 16 (hd = 40) and the keys >= M.
+struct QkParams {
+  int N, M, heads, hd, ksteps, bn, bufcols;
+  float scale;
+};
+constexpr int QK_A_BYTES = 128 * 128;            // 128 tokens x 64 channels bf16
+
+__global__ void __launch_bounds__(TC_THREADS)
+qkmax_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                const QkParams p, float* __restrict__ s_out, unsigned short* __restrict__ idx) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)p.bn * 128u;
+  const uint32_t stage_bytes = QK_A_BYTES + ((b_bytes + 1023u) & ~1023u);
+  const uint32_t bars = base + 2 * stage_bytes;
+  const uint32_t bar_full = bars, bar_empty = bars + 16, bar_tfull = bars + 32, bar_tempty = bars + 48;
+  const uint32_t tmem_slot = bars + 64;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, n0 = blockIdx.x * 128;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; i++) {
+      mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1);
+      mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * p.bufcols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int h = 0; h < p.heads; h++) {
+        const int st = h & 1;
+        mbar_wait(bar_empty + 8 * st, ((h >> 1) & 1) ^ 1);
+        const uint32_t sa = base + st * stage_bytes, bar = bar_full + 8 * st;
+        mbar_expect_tx(bar, QK_A_BYTES + b_bytes);
+        tma_load_3d(sa, &map_q, bar, h * p.hd, n0, b);
+        tma_load_4d(sa + QK_A_BYTES, &map_k, bar, 0, h, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.bn);
+      for (int h = 0; h < p.heads; h++) {
+        const int st = h & 1;
+        mbar_wait(bar_tempty + 8 * st, ((h >> 1) & 1) ^ 1);        // accumulator buffer drained
+        mbar_wait(bar_full + 8 * st, (h >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = base + st * stage_bytes, sb = sa + QK_A_BYTES;
+        for (int kk = 0; kk < p.ksteps; kk++)
+          umma_bf16_ss(tmem_base + (uint32_t)(st * p.bufcols), umma_desc_kmajor_sw128(sa + kk * 32),
+                       umma_desc_kmajor_sw128(sb + kk * 32), idesc, kk != 0);
+        umma_commit(bar_empty + 8 * st);
+        umma_commit(bar_tfull + 8 * st);
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int n = n0 + lg * 32 + lane;
+    float total = 0.f;
+    for (int h = 0; h < p.heads; h++) {
+      const int st = h & 1;
+      mbar_wait(bar_tfull + 8 * st, (h >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(st * p.bufcols);
+      float best = -INFINITY;
+      int besti = 0;
+      for (int c = 0; c < p.bn; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)c, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const float v = __uint_as_float(r[j]);
+          if (c + j < p.M && v > best) { best = v; besti = c + j; }      // first occurrence wins ties
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * st);
+      total += best;
+      if (n < p.N) idx[((long long)b * p.heads + h) * p.N + n] = (unsigned short)besti;
+    }
+    if (n < p.N) s_out[(long long)b * p.N + n] = total * p.scale;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * p.bufcols));
+  }
+}
+
+}  // namespace
+
+// returns 1 when the shape is not covered (caller falls back to the CUDA-core kernel), 0 on success, <0 on error
+extern "C" int crd_attn_qkmax_fwd_tc(const void* q, const void* k, float* s, unsigned short* idx, int B, int N, int M,
+                                     int C, int heads, float scale, crd_stream_t stream) {
+  CRD_REQUIRE(q && k && s && idx && heads > 0 && C % heads == 0);
+  const int hd = C / heads;
+  if (hd % 8 || hd > 64 || M > 256 || M < 1 || C % 8 || N < 1 || B < 1) return 1;
+  if (((uintptr_t)q & 15) || ((uintptr_t)k & 15)) return 1;
+  QkParams p;
+  p.N = N; p.M = M; p.heads = heads; p.hd = hd;
+  p.ksteps = (hd + 15) / 16;
+  p.bn = (M + 15) / 16 * 16;
+  p.bufcols = p.bn <= 32 ? 32 : (p.bn <= 64 ? 64 : (p.bn <= 128 ? 128 : 256));
+  p.scale = scale;
+  const int smem = 2 * (QK_A_BYTES + ((p.bn * 128 + 1023) & ~1023)) + 1024 + 128;
+  static unsigned long long attr = 0;
+  if (int e = ensure_smem_attr(qkmax_tc_kernel, 2 * (QK_A_BYTES + 32768) + 1024 + 128, attr)) return e;
+  CUtensorMap map_q, map_k;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)B};
+    cuuint64_t str[2] = {(cuuint64_t)C * 2, (cuuint64_t)N * C * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    if (int e = make_map(&map_q, q, 3, dims, str, box)) return e;
+  }
+  {
+    // per-head view with ascending strides: {channel in head, head, key, sample}
+    cuuint64_t dims[4] = {(cuuint64_t)hd, (cuuint64_t)heads, (cuuint64_t)M, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)hd * 2, (cuuint64_t)C * 2, (cuuint64_t)M * C * 2};
+    cuuint32_t box[4] = {64, 1, (cuuint32_t)p.bn, 1};
+    if (int e = make_map(&map_k, k, 4, dims, str, box)) return e;
+  }
+  qkmax_tc_kernel<<<dim3((N + 127) / 128, B), TC_THREADS, smem, (cudaStream_t)stream>>>(map_q, map_k, p, s, idx);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
