@@ -803,9 +803,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         }
         else { cc = c0 + 64 * j + col; kbase = cc; }
         float* dst = dw + (long long)co * p.Ktot + kbase;
+        if (cc + 16 <= p.Cin && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          // split-K partials meet in L2: four 16-byte vector reductions instead of sixteen scalar ones
 #pragma unroll
-        for (int q = 0; q < 16; q++)
-          if (cc + q < p.Cin) atomicAdd(dst + q, __uint_as_float(r[q]));
+          for (int q = 0; q < 16; q += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q), "f"(__uint_as_float(r[q])),
+                         "f"(__uint_as_float(r[q + 1])), "f"(__uint_as_float(r[q + 2])), "f"(__uint_as_float(r[q + 3]))
+                         : "memory");
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; q++)
+            if (cc + q < p.Cin) atomicAdd(dst + q, __uint_as_float(r[q]));
+        }
       }
     }
   }
@@ -883,13 +892,32 @@ extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const vo
   if (rc) return rc;
   const int gy = p.flat ? (p.kchunks + 2) / 3 : p.kchunks * p.KH;
   const int gz = (d->Cout + 127) / 128;
-  // split the pixel tiles so that ~2 waves of CTAs cover the 148 SMs; each split handles >= 4 tiles
-  static int wg_target = 0;
-  if (!wg_target) { const char* e = getenv("CAMRADEPTH_WG_CTAS"); wg_target = e ? atoi(e) : 296; if (wg_target < 1) wg_target = 296; }
-  long long want = ((long long)wg_target + (long long)gy * gz - 1) / ((long long)gy * gz);
-  long long maxs = (p.total_tiles + 7) / 8;
-  long long splits = want < 1 ? 1 : (want > maxs ? maxs : want);
-  if (splits < 1) splits = 1;
+  // Split-K over the pixel tiles.  One CTA per SM is resident (200 KB ring), so the launch runs in waves of
+  // sm_count CTAs: pick the split count minimising waves * (tiles per CTA + fixed prologue/epilogue cost, in
+  // tile units) -- e.g. 15 work columns x 20 splits = 300 CTAs would spill 4 CTAs into a third wave.
+  static int wg_over = -1, wg_fixed = 0;
+  if (wg_over < 0) {
+    const char* e = getenv("CAMRADEPTH_WG_OVERHEAD"); wg_over = e ? atoi(e) : 6; if (wg_over < 0) wg_over = 6;
+    const char* f = getenv("CAMRADEPTH_WG_CTAS"); wg_fixed = f ? atoi(f) : 0;
+  }
+  const long long cols = (long long)gy * gz, sms = sm_count();
+  long long maxs = (p.total_tiles + 3) / 4;
+  if (maxs < 1) maxs = 1;
+  long long splits = 1;
+  if (wg_fixed > 0) {
+    splits = (wg_fixed + cols - 1) / cols;
+    if (splits > maxs) splits = maxs;
+  } else {
+    long long best_cost = -1;
+    const long long smax = maxs < 4 * sms ? maxs : 4 * sms;
+    for (long long sp = 1; sp <= smax; sp++) {
+      const long long tps = (p.total_tiles + sp - 1) / sp;
+      const long long ctas = cols * ((p.total_tiles + tps - 1) / tps);
+      const long long waves = (ctas + sms - 1) / sms;
+      const long long cost = waves * (tps + wg_over);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; splits = sp; }
+    }
+  }
   p.tiles_per_split = (p.total_tiles + splits - 1) / splits;
   splits = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   const dim3 grid((unsigned)splits, gy, gz);
