@@ -83,30 +83,38 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // exact-erf GELU (nn.GELU default).  erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below fp32
 // GroupNorm noise) so value and derivative share ONE exponential: exp(-x^2/2) is both the erf tail and the
-// Gaussian pdf.  ~12 FP32 ops + 1 MUFU.EX2 + 1 MUFU.RCP instead of the ~40-op erff().
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
+// Gaussian pdf.  ~13 FP32 ops + 1 MUFU.EX2 + 1 MUFU.RCP instead of the ~40-op erff().
+// MUFU.RCP without the IEEE-rounding fix-up (and its slow-path call) of __frcp_rn / operator/: 1 ulp
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// h = 0.5 * erfc(|x| / sqrt2) (the Gaussian tail beyond |x|) and e = exp(-x^2 / 2)
+__device__ __forceinline__ void gelu_tail(float x, float& h, float& e) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  const float e = __expf(-z * z);                                  // = exp(-x^2/2)
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  const float erfz = 1.0f - poly * t * e;                          // erf(|x|/sqrt2)
-  cdf = 0.5f * (1.0f + copysignf(erfz, x));
-  pdf = 0.39894228040143267794f * e;
+  const float t = rcp_fast(fmaf(0.3275911f, z, 1.0f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));   // exp(-x^2/2)
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(t, poly, 0.5f * 1.421413741f);
+  poly = fmaf(t, poly, 0.5f * -0.284496736f);
+  poly = fmaf(t, poly, 0.5f * 0.254829592f);
+  h = poly * t * e;
 }
+// gelu(x) = x * Phi(x) = relu(x) - |x| * h: no cancellation in either tail
 __device__ __forceinline__ float gelu_f(float x) {
-  float cdf, pdf;
-  gelu_parts(x, cdf, pdf);
-  return x * cdf;
+  float h, e;
+  gelu_tail(x, h, e);
+  return fmaxf(x, 0.f) - fabsf(x * h);
 }
+// gelu'(x) = Phi(x) + x * phi(x)
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  float cdf, pdf;
-  gelu_parts(x, cdf, pdf);
-  return fmaf(x, pdf, cdf);
+  float h, e;
+  gelu_tail(x, h, e);
+  const float cdf = x > 0.f ? 1.0f - h : h;
+  return fmaf(x * e, 0.39894228040143267794f, cdf);
 }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_fast(1.0f + __expf(-x)); }
 
 static inline int crd_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -2,12 +2,12 @@
 //
 // The register-staged kernels in norm_act.cu keep their in-flight loads in registers, so bytes in flight are
 // capped by occupancy (122-175 registers per thread -> 32-64 KB per SM, measured 2.2-3.9 TB/s).  Here a
-// producer warp streams {CW channels x PH pixels} boxes of each input through a ring of 8-KiB shared-memory
-// slots with cp.async.bulk.tensor + mbarriers (96 KiB in flight per CTA, two CTAs per SM), and 256 consumer
+// producer warp streams {CW channels x PH pixels} boxes of each input through a ring of 16-KiB shared-memory
+// slots with cp.async.bulk.tensor + mbarriers (96 KiB in flight per CTA, two CTAs per SM), and 224 consumer
 // threads read their 16-byte pieces from shared memory, so the HBM queue depth no longer depends on registers.
 //   grid  = (pixel splits, C / CW, B);  one CTA owns a (sample, channel tile, pixel range) and keeps the
 //           per-(b,c) constants of its 8 channels per thread in registers, like the register-staged kernels
-//   block = 8 consumer warps laid out (cvec = CW/8, rows) + 1 producer warp
+//   block = 7 consumer warps laid out (cvec = CW/8, rows) + 1 producer warp
 // Out-of-range pixels of the last tile are zero-filled by the TMA unit and masked by the consumers.
 #pragma once
 #include <stdlib.h>
@@ -17,11 +17,11 @@
 
 namespace {
 
-constexpr int ST_SLOT = 8192;          // bytes per tile slot
-constexpr int ST_SLOTS = 12;           // 96 KiB ring
-constexpr int ST_CONSUMERS = 256;
+constexpr int ST_SLOT = 16384;         // bytes per tile slot
+constexpr int ST_SLOTS = 6;            // 96 KiB ring
+constexpr int ST_CONSUMERS = 224;          // 7 warps + 1 producer warp = 256 threads: 128 registers at 2 CTAs/SM
 constexpr int ST_THREADS = ST_CONSUMERS + 32;
-constexpr int ST_R = 2;                // pixel rows per consumer thread per tile
+constexpr int ST_R = 4;                // pixel rows per consumer thread per tile (independent chains per thread)
 constexpr int ST_SMEM = ST_SLOTS * ST_SLOT + 256 + 128;
 
 enum { ST_STATS = 0, ST_AFFINE = 1, ST_BWD_REDUCE = 2, ST_BWD_APPLY = 3 };
