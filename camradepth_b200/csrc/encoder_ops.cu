@@ -321,23 +321,30 @@ __global__ void attn_qkmax_bwd_kernel(const float* __restrict__ ds, const T* __r
 #pragma unroll
     for (int j = 0; j < 8; j++) o[j] = g * kv[j];
     store8(dq + tok * C + c, o);
-    float* dkp = dk + ((long long)b * M + m) * C + c;
+    float* dkp = dk + ((long long)b * M + m) * C + c;              // 32-byte aligned: two 16-byte vector reductions
 #pragma unroll
-    for (int j = 0; j < 8; j++) atomicAdd(dkp + j, g * qv[j]);
+    for (int j = 0; j < 8; j += 4)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dkp + j), "f"(g * qv[j]), "f"(g * qv[j + 1]),
+                   "f"(g * qv[j + 2]), "f"(g * qv[j + 3])
+                   : "memory");
   }
 }
 
 // ------------------------------------------------------------------ proj applied to the token mean
-__global__ void attn_pv_fwd_kernel(const float* __restrict__ xbar, const float* __restrict__ Wp,
-                                   float* __restrict__ pv, int B, int C) {
-  const int b = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int o = warp; o < C; o += nw) {
-    float acc = 0.f;
-    for (int c = lane; c < C; c += 32) acc = fmaf(Wp[(long long)o * C + c], xbar[(long long)b * C + c], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) pv[(long long)b * C + o] = acc;
-  }
+// one warp per (sample, output channel): B*C warps in flight instead of B blocks walking C outputs serially
+__global__ void __launch_bounds__(256) attn_pv_fwd_kernel(const float* __restrict__ xbar, const float* __restrict__ Wp,
+                                                          float* __restrict__ pv, int B, int C) {
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 8 + warp;
+  if (o >= C) return;
+  const float* wr = Wp + (long long)o * C;
+  const float* xr = xbar + (long long)b * C;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int c = lane; c < C; c += 32) acc = fmaf(wr[c], xr[c], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) pv[(long long)b * C + o] = acc;
 }
 __global__ void attn_pv_bwd_w_kernel(const float* __restrict__ dpv, const float* __restrict__ xbar, float* dWp,
                                      int B, int C) {
@@ -345,17 +352,30 @@ __global__ void attn_pv_bwd_w_kernel(const float* __restrict__ dpv, const float*
   if (i >= (long long)C * C) return;
   const int o = (int)(i / C), c = (int)(i % C);
   float acc = 0.f;
+#pragma unroll 8
   for (int b = 0; b < B; b++) acc = fmaf(dpv[(long long)b * C + o], xbar[(long long)b * C + c], acc);
   dWp[i] += acc;
 }
-__global__ void attn_pv_bwd_x_kernel(const float* __restrict__ dpv, const float* __restrict__ Wp,
-                                     float* __restrict__ dxbar, float scale, int B, int C) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)B * C) return;
-  const int b = (int)(i / C), c = (int)(i % C);
+// block (32 channels, 8 slices of the output-channel sum) per (channel tile, sample)
+__global__ void __launch_bounds__(256) attn_pv_bwd_x_kernel(const float* __restrict__ dpv, const float* __restrict__ Wp,
+                                                            float* __restrict__ dxbar, float scale, int B, int C) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, os = threadIdx.x >> 5;
+  const int b = blockIdx.y, c = blockIdx.x * 32 + cl;
   float acc = 0.f;
-  for (int o = 0; o < C; o++) acc = fmaf(Wp[(long long)o * C + c], dpv[(long long)b * C + o], acc);
-  dxbar[i] = acc * scale;
+  if (c < C) {
+    const float* g = dpv + (long long)b * C;
+#pragma unroll 8
+    for (int o = os; o < C; o += 8) acc = fmaf(Wp[(long long)o * C + c], g[o], acc);
+  }
+  red[os][cl] = acc;
+  __syncthreads();
+  if (os == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) t += red[k][cl];
+    dxbar[(long long)b * C + c] = t * scale;
+  }
 }
 
 __global__ void attn_out_residual_kernel(const float* __restrict__ x, const float* __restrict__ pv,
@@ -562,7 +582,7 @@ extern "C" int crd_attn_qkmax_bwd(const float* ds, const void* q, const void* k,
 }
 extern "C" int crd_attn_pv_fwd(const float* xbar, const float* Wp, float* pv, int B, int C, crd_stream_t stream) {
   if (B == 0) return 0;
-  attn_pv_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(xbar, Wp, pv, B, C);
+  attn_pv_fwd_kernel<<<dim3(crd_div_up(C, 8), B), 256, 0, (cudaStream_t)stream>>>(xbar, Wp, pv, B, C);
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -571,7 +591,7 @@ extern "C" int crd_attn_pv_bwd(const float* dpv, const float* xbar, const float*
   if (B == 0) return 0;
   attn_pv_bwd_w_kernel<<<crd_div_up((long long)C * C, 256), 256, 0, (cudaStream_t)stream>>>(dpv, xbar, dWp, B, C);
   CRD_LAUNCH_CHECK();
-  attn_pv_bwd_x_kernel<<<crd_div_up((long long)B * C, 256), 256, 0, (cudaStream_t)stream>>>(dpv, Wp, dxbar, dxbar_scale, B, C);
+  attn_pv_bwd_x_kernel<<<dim3(crd_div_up(C, 32), B), 256, 0, (cudaStream_t)stream>>>(dpv, Wp, dxbar, dxbar_scale, B, C);
   CRD_LAUNCH_CHECK();
   return 0;
 }

@@ -82,6 +82,8 @@ class Engine:
         self.names = list(self.P.keys())
         self.device = None
         self._packs = {}
+        self._pack_jobs = {}        # key -> ([(param name, dst view, cmap, Cout, Cin, taps, Cin_p, Cout_p, mode)], ver fn)
+        self._pack_table = None     # (signature, device table, n items, n blocks)
         self._maps = {}
         self.use_tc = precision == "bf16" and os.environ.get("CAMRADEPTH_TC", "1") == "1"
         self.use_tc_wgrad = self.use_tc and os.environ.get("CAMRADEPTH_TC_WGRAD", "1") == "1"
@@ -201,7 +203,37 @@ class Engine:
         ops.weight_pack(p.detach(), dst, self._cmap(name), L["cout"], L["cin"], L["taps"], L["cin_p"], L["cout_p"],
                         mode)
         self._packs[key] = (dst, ver)
+        self._pack_jobs[key] = ([(name, dst, self._cmap(name), L["cout"], L["cin"], L["taps"], L["cin_p"],
+                                  L["cout_p"], mode)],
+                                lambda: (p._version, p.data_ptr(), WEIGHT_EPOCH[0], self._grad_epoch))
         return dst
+
+    def prepack(self):
+        """Refresh every packed weight copy seen so far with ONE kernel launch (instead of ~380 per training
+        step).  Called when the packed copies go stale: at the start of each grad-enabled forward."""
+        if not self._pack_jobs:
+            return
+        jobs = [j for js, _ in self._pack_jobs.values() for j in js]
+        sig = tuple((self.P[j[0]].data_ptr(), j[1].data_ptr()) for j in jobs)
+        if (self._pack_table is None or self._pack_table[0] != sig) and torch.cuda.is_current_stream_capturing():
+            # building the device table needs a host->device copy, which a capturing stream cannot take
+            for (name, dst, cmap, cout, cin, taps, cin_p, cout_p, mode) in jobs:
+                ops.weight_pack(self.P[name].detach(), dst, cmap, cout, cin, taps, cin_p, cout_p, mode)
+        elif self._pack_table is None or self._pack_table[0] != sig:
+            rows, blk = [], 0
+            for (name, dst, cmap, cout, cin, taps, cin_p, cout_p, mode) in jobs:
+                total = cout * cin * taps
+                rows.append([self.P[name].data_ptr(), dst.data_ptr(), 0 if cmap is None else cmap.data_ptr(), blk,
+                             cout, cin, taps, cin_p, cout_p, mode, ops.dcode(dst), total])
+                blk += (total + 1023) // 1024
+            rows.append([0, 0, 0, blk] + [0] * 8)
+            table = torch.tensor(rows, dtype=torch.int64).to(self.device)
+            self._pack_table = (sig, table, len(jobs), blk)
+        if self._pack_table is not None and self._pack_table[0] == sig:
+            _, table, n, blk = self._pack_table
+            ops.weight_pack_batch(table, n, blk)
+        for key, (js, verfn) in self._pack_jobs.items():
+            self._packs[key] = (self._packs[key][0], verfn())
 
     def _tc_ok(self, L, x, y_or_dy):
         """tcgen05 path: bf16 operands, stride-1 'same' KxK or 1x1 contractions."""
@@ -529,11 +561,15 @@ class Engine:
         dst = ent[0] if ent is not None and ent[0].device == self.device else \
             torch.zeros(ct, 9 * ktot, dtype=self.tdtype, device=self.device)
         flat = dst.view(-1)
+        jobs = []
         for li, n in enumerate(names):
             L = self.L[n]
             ops.weight_pack(ps[li].detach(), flat[self.DY_OFF[li]:], self._cmap(n), L["cout"], L["cin"], 9,
                             L["cin_p"], ktot, 1)
+            jobs.append((n, flat[self.DY_OFF[li]:], self._cmap(n), L["cout"], L["cin"], 9, L["cin_p"], ktot, 1))
         self._packs[key] = (dst, ver)
+        self._pack_jobs[key] = (jobs, lambda: tuple((p._version, p.data_ptr()) for p in ps) +
+                                (WEIGHT_EPOCH[0], self._grad_epoch))
         return dst
 
     def dec_bwd(self, prefix, rec, ddest, dsrc, src_accumulate):
@@ -628,6 +664,7 @@ class Engine:
             # training forward: parameters may have been updated through `.data` (no version bump, e.g. the
             # reference's own optimizer), so packed copies are rebuilt every grad-enabled forward
             self._grad_epoch += 1
+            self.prepack()
         self.fwd_arena.reset()
         if train:
             dps, d2s = masks if masks is not None else self.make_masks(B)

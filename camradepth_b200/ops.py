@@ -105,6 +105,10 @@ def weight_pack(w, dst, cmap, Cout, Cin, taps, Cin_p, Cout_p, mode):
     K.crd_weight_pack(P(w), P(dst), dcode(dst), P(cmap), Cout, Cin, taps, Cin_p, Cout_p, mode, stream())
 
 
+def weight_pack_batch(table, n_items, n_blocks):
+    K.crd_weight_pack_batch(P(table), n_items, n_blocks, stream())
+
+
 def weight_unpack_grad(dwp, grad, cmap, Cout, Cin, taps, Cin_p, accumulate):
     K.crd_weight_unpack_grad(P(dwp), P(grad), P(cmap), Cout, Cin, taps, Cin_p, int(accumulate), stream())
 

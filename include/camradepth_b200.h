@@ -92,6 +92,10 @@ CRD_API int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const void*
  * map == NULL is the identity; dst must be zero-filled by the caller where unmapped. */
 CRD_API int crd_weight_pack(const float* w, void* dst, int dst_dtype, const int* map, int Cout, int Cin, int taps,
                     int Cin_p, int Cout_p, int mode, crd_stream_t stream);
+/* All packed copies in one launch (refresh after an optimizer step, runner.py:232).  `table` is a DEVICE array of
+ * n_items + 1 rows of 12 int64: {w, dst, map, first block, Cout, Cin, taps, Cin_p, Cout_p, mode, dst dtype,
+ * Cout*Cin*taps}; an item owns ceil(elements / 1024) consecutive blocks and row n_items holds n_blocks. */
+CRD_API int crd_weight_pack_batch(const long long* table, int n_items, int n_blocks, crd_stream_t stream);
 /* Strided convolutions (patch embeddings k7s4/k3s2, spatial-reduction convs k=s; simplified_attention.py:68,
  * 158-160) run as GEMMs on the tensor-core path: gather the patches once, multiply, scatter the data gradient.
  * col is [B*Ho*Wo][KH*KW*Cin]; col2im is the gather-form adjoint. */
