@@ -692,18 +692,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
 
   // work column: (chunk, kh) for KxK; a group of up to 3 chunks for 1x1
   int c0, kh = 0, nblk;       // in halo mode `kh` holds the CTA's kw and the N blocks are the three kh taps
+  // blockIdx.x = work column (fastest varying), blockIdx.y = pixel split: the CTAs resident at the same time
+  // cover ALL columns of a few pixel ranges, so a dY / X tile fetched from HBM by one column is an L2 hit for
+  // the others (with the split index fastest, each wave of columns re-streamed both tensors: 5.5x the bytes)
   if (p.KH > 1) {
-    const int chunk = blockIdx.y / p.KH;
-    kh = blockIdx.y - chunk * p.KH;
+    const int chunk = blockIdx.x / p.KH;
+    kh = blockIdx.x - chunk * p.KH;
     c0 = chunk * 64;
     nblk = p.KW;
   } else {
-    c0 = blockIdx.y * 192;
-    nblk = min(3, p.kchunks - blockIdx.y * 3);
+    c0 = blockIdx.x * 192;
+    nblk = min(3, p.kchunks - (int)blockIdx.x * 3);
   }
   const int co0 = blockIdx.z * 128;
   const int mblocks = min(p.mblocks, (p.Cout - co0 + 63) / 64);
-  const long long t_begin = (long long)blockIdx.x * p.tiles_per_split;
+  const long long t_begin = (long long)blockIdx.y * p.tiles_per_split;
   const long long t_end = min(p.total_tiles, t_begin + p.tiles_per_split);
   const int ntiles = (int)max(0LL, t_end - t_begin);
 
@@ -920,7 +923,7 @@ extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const vo
   }
   p.tiles_per_split = (p.total_tiles + splits - 1) / splits;
   splits = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  const dim3 grid((unsigned)splits, gy, gz);
+  const dim3 grid(gy, (unsigned)splits, gz);
   cudaStream_t st = (cudaStream_t)stream;
   if (WG_PIX == 32) wgrad_tc_kernel<32><<<grid, TC_THREADS, WG_SMEM, st>>>(map_dy, map_x, p, dw);
   else if (WG_PIX == 64) wgrad_tc_kernel<64><<<grid, TC_THREADS, WG_SMEM, st>>>(map_dy, map_x, p, dw);

@@ -27,7 +27,7 @@ def report(name, ms, nbytes):
     print(f"{name:44s} {ms*1e3:9.1f} us  {nbytes/ms/1e6:8.1f} GB/s  ({nbytes/1e6:.0f} MB)")
 
 
-SHAPES = [(32, 192 * 416, 128, 296), (32, 192 * 416, 96, 296), (32, 96 * 208, 128, 296), (32, 48 * 104, 512, 512),
+SHAPES = [(32, 192 * 416, 128, 320), (32, 192 * 416, 96, 320), (32, 96 * 208, 128, 320), (32, 48 * 104, 512, 512),
           (32, 24 * 52, 1024, 1024), (32, 12 * 26, 640, 640), (32, 48 * 104, 64, 64)]
 for (B, N, C, ld) in SHAPES:
     x = torch.randn(B, N, C, device=d).to(BF)
@@ -56,6 +56,14 @@ for (B, N, C, ld) in SHAPES:
         bias = torch.randn(C, device=d)
         dw, db = torch.zeros(C, 9, device=d), torch.zeros(C, device=d)
         report("dwconv_fwd " + tag, timeit(lambda: ops.dwconv_fwd(x4, ab, w, bias, o4)), 2 * e)
-        report("dwconv_bwd_input " + tag, timeit(lambda: ops.dwconv_bwd_input(x4, w, o4)), 2 * e)
-        report("dwconv_bwd_weight " + tag, timeit(lambda: ops.dwconv_bwd_weight(x4, x4, ab, dw, db)), 2 * e)
+        report("dwconv_bwd (fused) " + tag, timeit(lambda: ops.dwconv_bwd(x4, x4, ab, w, o4, dw, db)), 3 * e)
     del x, big, dy, out
+
+# bicubic x2 into / out of a channel slice of the concat buffer (decoder stage 4: 96x208 -> 192x416, 136 channels)
+Bq, Hq, Wq, Cq, ldq = 32, 96, 208, 136, 320
+src = torch.randn(Bq, Hq, Wq, Cq, device=d).to(BF)
+cat = torch.randn(Bq, 2 * Hq, 2 * Wq, ldq, device=d).to(BF)
+dsrc = torch.empty_like(src)
+eb = Bq * Hq * Wq * Cq * 2
+report("bicubic2x_fwd [B32 96x208 C136 -> ld320]", timeit(lambda: ops.bicubic2x_fwd(src, cat[..., :Cq])), 5 * eb)
+report("bicubic2x_bwd [B32 192x416 C136 ld320 ->]", timeit(lambda: ops.bicubic2x_bwd(cat[..., :Cq], dsrc, False)), 5 * eb)

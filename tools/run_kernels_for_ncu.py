@@ -1,6 +1,6 @@
 """Runs the dominant kernels in isolation at the BASELINE shapes so `ncu --set full` can capture them:
-the depth_upsample[4] layer-2 convolution (fwd / dgrad / wgrad, B=32 at 192x416) and one stage-2 Mix-FFN
-depthwise conv + GroupNorm backward."""
+the depth_upsample[4] layer-2 convolution (fwd / dgrad / wgrad, B=32 at 192x416), the TMA-staged streaming
+kernels (GroupNorm passes, depthwise 3x3, bicubic x2) and the tcgen05 attention score."""
 import math
 import os
 import sys
@@ -22,7 +22,7 @@ for _ in range(int(os.environ.get("CONV_ITERS", "3"))):
     ops.conv_fwd(ops.make_desc(x, y, Cin, Cout, 3, 3, 1, 1), x, w, None, y, use_tc=True)
     ops.conv_fwd(ops.make_desc(y, dx, Cout, Cin, 3, 3, 1, 1, transposed=1), y, wd, None, dx, use_tc=True)
     ops.conv_wgrad(ops.make_desc(x, y, Cin, Cout, 3, 3, 1, 1), x, y, dw, use_tc=True)
-# stage-2 Mix-FFN pieces
+# stage-2 Mix-FFN pieces (TMA-staged streaming kernels) and the attention score
 Bh, Hh, Wh, C = 32, 24, 52, 1024
 h = torch.randn(Bh, Hh, Wh, C, device=d).to(BF)
 g = torch.randn(Bh, Hh, Wh, C, device=d).to(BF)
@@ -32,13 +32,35 @@ wdw = torch.randn(C, 9, device=d)
 bias = torch.randn(C, device=d)
 coef = torch.randn(Bh, C, 3, device=d)
 pq = torch.zeros(Bh, C, 2, device=d)
+sums = torch.zeros(Bh, C, 2, device=d)
 dwg, dbg = torch.zeros(C, 9, device=d), torch.zeros(C, device=d)
-for _ in range(3):
+q = torch.randn(Bh, Hh * Wh, 128, device=d).to(BF)
+k = torch.randn(Bh, 78, 128, device=d).to(BF)
+sc = torch.empty(Bh, Hh * Wh, device=d)
+idx = torch.empty(Bh, 2, Hh * Wh, dtype=torch.int16, device=d)
+# full-resolution decoder pieces: GroupNorm passes over a 128-channel slice of the 320-channel concat buffer and
+# the bicubic x2 that feeds it
+cat = torch.randn(B, H, W, 320, device=d).to(BF)
+dcat = torch.randn(B, H, W, 320, device=d).to(BF)
+src = torch.randn(B, H // 2, W // 2, 136, device=d).to(BF)
+dsrc = torch.empty_like(src)
+ab2 = torch.randn(B, 128, 2, device=d)
+coef2 = torch.randn(B, 128, 3, device=d)
+pq2 = torch.zeros(B, 128, 2, device=d)
+sums2 = torch.zeros(B, 128, 2, device=d)
+for _ in range(2):
     ops.dwconv_fwd(h, ab, wdw, bias, o)
-    ops.dwconv_bwd_input(g, wdw, o)
-    ops.dwconv_bwd_weight(g, h, ab, dwg, dbg)
-    ops.gnact_bwd_reduce(g, h, ab, None, None, ops.ACT_GELU, pq)
-    ops.gnact_bwd_apply(g, h, ab, None, None, ops.ACT_GELU, coef, o, False)
+    ops.dwconv_bwd(g, h, ab, wdw, o, dwg, dbg)
+    ops.chan_stats(h, sums)
     ops.affine_act(h, o, ab, None, ops.ACT_GELU)
+    ops.gnact_bwd_reduce(g, h, ab, None, None, ops.ACT_GELU, pq, g)
+    ops.gnact_bwd_apply(g, h, ab, None, None, ops.ACT_NONE, coef, o, False)
+    ops.attn_qkmax_fwd(q, k, sc, idx, 2, 64 ** -0.5)
+    ops.chan_stats(y, sums2)
+    ops.affine_act(y, cat[..., 192:320], ab2, None, ops.ACT_GELU)
+    ops.gnact_bwd_reduce(dcat[..., 192:320], y, ab2, None, None, ops.ACT_GELU, pq2, dcat[..., 192:320])
+    ops.gnact_bwd_apply(dcat[..., 192:320], y, ab2, None, None, ops.ACT_NONE, coef2, y, False)
+    ops.bicubic2x_fwd(src, cat[..., :136])
+    ops.bicubic2x_bwd(dcat[..., :136], dsrc, False)
 torch.cuda.synchronize()
 print("done")
