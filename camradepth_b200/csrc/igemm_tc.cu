@@ -659,6 +659,7 @@ struct WgParams {
   int Cin, Cout, kchunks;
   int mblocks;              // 64-channel blocks of dY in this launch (1 or 2)
   int halo;                 // 3x3: one X box with TH+2 rows per (chunk, kw); the kh taps are its 2-KiB row offsets
+  int bias;                 // 1x1 only: also produce db[co] = sum_px dY (an extra N=64 MMA against a tile of ones)
   long long Ktot;           // row stride of dw
 };
 
@@ -677,11 +678,12 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t saddr, uint
 template <int WG_PIX>          // pixels (GEMM-K) per pipeline stage: 32, 64 or 128
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
-                const WgParams p, float* __restrict__ dw) {
+                const WgParams p, float* __restrict__ dw, float* __restrict__ db) {
   constexpr int WG_BLK_BYTES = WG_PIX * 64 * 2;
   constexpr int WG_HALO_X_BYTES = (WG_PIX / 16 + 2) * 16 * 128;   // X box with two halo rows (TW = 16)
   const int WG_STAGE_BYTES = p.halo ? 2 * WG_BLK_BYTES + WG_HALO_X_BYTES : 5 * WG_BLK_BYTES;
-  const int WG_STAGES = min(WG_MAX_STAGES, (200 * 1024) / WG_STAGE_BYTES);
+  // with the bias reduction the last 16 KiB of the 200 KiB hold the constant tile of ones (B operand of db)
+  const int WG_STAGES = min(WG_MAX_STAGES, ((p.bias ? 183 : 200) * 1024) / WG_STAGE_BYTES);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + WG_STAGES * WG_STAGE_BYTES;
@@ -706,6 +708,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   }
   const int co0 = blockIdx.z * 128;
   const int mblocks = min(p.mblocks, (p.Cout - co0 + 63) / 64);
+  const bool do_bias = p.bias && blockIdx.x == 0;           // one work column per (split, Cout block) sums dY
+  const uint32_t ones = base + 184 * 1024;
+  if (do_bias) {
+    // bf16 1.0 everywhere: invariant under the 128B swizzle, so no layout arithmetic
+    for (int i = threadIdx.x; i < 16384 / 16; i += TC_THREADS)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ones + i * 16), "r"(0x3F803F80u) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   const long long t_begin = (long long)blockIdx.y * p.tiles_per_split;
   const long long t_end = min(p.total_tiles, t_begin + p.tiles_per_split);
   const int ntiles = (int)max(0LL, t_end - t_begin);
@@ -770,6 +780,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       if (lane == 0) {
         // M = 128 (rows beyond the loaded dY blocks hold stale smem and are ignored by the epilogue)
         const uint32_t idesc = umma_idesc_bf16(128, nblk * 64) | (1u << 15) | (1u << 16);   // A, B MN-major
+        const uint32_t idesc1 = umma_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);
         for (int it = 0; it < ntiles; it++) {
           const int s = it % WG_STAGES;
           const uint32_t ph = (it / WG_STAGES) & 1;
@@ -782,6 +793,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             // halo mode: N block j = tap kh=j = the same box shifted by j image rows (16 px * 128 B = 2 KiB)
             const uint64_t bd = umma_desc_mnmajor_sw128(sb + k * 2048, p.halo ? 2048u : (uint32_t)WG_BLK_BYTES);
             umma_bf16_ss(tmem_base, ad, bd, idesc, (it | k) != 0);
+            if (do_bias)          // columns 192..255: every column = sum over the pixels of dY
+              umma_bf16_ss(tmem_base + 192, ad, umma_desc_mnmajor_sw128(ones + k * 2048, WG_BLK_BYTES), idesc1,
+                           (it | k) != 0);
           }
           umma_commit(bar_empty + 8 * s);
         }
@@ -819,6 +833,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             if (cc + q < p.Cin) atomicAdd(dst + q, __uint_as_float(r[q]));
         }
       }
+      if (do_bias) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + 192u, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (co < p.Cout && lg * 32 + lane < mblocks * 64) atomicAdd(db + co, __uint_as_float(r[0]));
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -830,9 +850,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
 
 }  // namespace
 
-extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const void* dy, float* dw,
-                                 crd_stream_t stream) {
+static int conv_wgrad_tc_impl(const crd_conv_desc* d, const void* x, const void* dy, float* dw, float* db,
+                              crd_stream_t stream) {
   CRD_REQUIRE(d && x && dy && dw);
+  CRD_REQUIRE(db == nullptr || d->KH == 1);              // the fused bias reduction exists for 1x1 contractions
   CRD_REQUIRE(d->in_dtype == CRD_BF16 && d->out_dtype == CRD_BF16);
   CRD_REQUIRE(d->stride == 1 && !d->transposed && d->Ho == d->H && d->Wo == d->W);
   CRD_REQUIRE(d->Cin % 8 == 0 && d->ldx % 8 == 0 && d->ldy % 8 == 0);
@@ -865,6 +886,7 @@ extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const vo
   static int wg_halo = -1;
   if (wg_halo < 0) { const char* e = getenv("CAMRADEPTH_WG_HALO"); wg_halo = (e && e[0] == '0') ? 0 : 1; }
   p.halo = (wg_halo && d->KH == 3 && d->W >= 16) ? 1 : 0;
+  p.bias = db != nullptr;
   p.TW = d->W >= 16 ? 16 : (d->W >= 8 ? 8 : 4);
   p.TH = WG_PIX / p.TW;
   p.tiles_w = (d->W + p.TW - 1) / p.TW;
@@ -925,11 +947,22 @@ extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const vo
   splits = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   const dim3 grid(gy, (unsigned)splits, gz);
   cudaStream_t st = (cudaStream_t)stream;
-  if (WG_PIX == 32) wgrad_tc_kernel<32><<<grid, TC_THREADS, WG_SMEM, st>>>(map_dy, map_x, p, dw);
-  else if (WG_PIX == 64) wgrad_tc_kernel<64><<<grid, TC_THREADS, WG_SMEM, st>>>(map_dy, map_x, p, dw);
-  else wgrad_tc_kernel<128><<<grid, TC_THREADS, WG_SMEM, st>>>(map_dy, map_x, p, dw);
+  if (WG_PIX == 32) wgrad_tc_kernel<32><<<grid, TC_THREADS, WG_SMEM, st>>>(map_dy, map_x, p, dw, db);
+  else if (WG_PIX == 64) wgrad_tc_kernel<64><<<grid, TC_THREADS, WG_SMEM, st>>>(map_dy, map_x, p, dw, db);
+  else wgrad_tc_kernel<128><<<grid, TC_THREADS, WG_SMEM, st>>>(map_dy, map_x, p, dw, db);
   CRD_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const void* dy, float* dw,
+                                 crd_stream_t stream) {
+  return conv_wgrad_tc_impl(d, x, dy, dw, nullptr, stream);
+}
+// 1x1 contraction: dw += dY^T X and db += column sums of dY from the same pass over dY
+extern "C" int crd_conv_wgrad_bias_tc(const crd_conv_desc* d, const void* x, const void* dy, float* dw, float* db,
+                                      crd_stream_t stream) {
+  CRD_REQUIRE(db != nullptr);
+  return conv_wgrad_tc_impl(d, x, dy, dw, db, stream);
 }
 
 namespace {

@@ -288,20 +288,26 @@ class Engine:
         direct = L["taps"] == 1 and L["cmap"] is None and L["cin_p"] == L["cin"]
         g = self.pg[name]
         dwp = g.view(L["cout"], L["cin"]) if direct else self.bwd_arena.take(L["cout"], L["taps"] * L["cin_p"])
+        db = self.pg[bias] if bias is not None else None
         if self._gemm_route(L, x) and self.use_tc_wgrad:
             col = self._im2col(L, x, dy.shape[1], dy.shape[2])      # recomputed: cheaper than keeping it alive
             d = ops.make_desc(col, dy, col.shape[-1], L["cout"], 1, 1, 1, 0)
-            ops.conv_wgrad(d, col, dy, dwp, use_tc=True)
+            ops.conv_wgrad(d, col, dy, dwp, use_tc=True, db=db)     # bias gradient from the same pass over dy
+            db = None
         else:
             d = ops.make_desc(x, dy, L["cin_p"], L["cout"], L["k"], L["k"], L["stride"], L["pad"], 0, 0, 0, 0)
             ev = self._timed("wgrad", name)
-            ops.conv_wgrad(d, x, dy, dwp, use_tc=self.use_tc_wgrad and self._tc_ok(L, x, dy))
+            tc = self.use_tc_wgrad and self._tc_ok(L, x, dy)
+            fused = tc and L["k"] == 1 and db is not None
+            ops.conv_wgrad(d, x, dy, dwp, use_tc=tc, db=db if fused else None)
+            if fused:
+                db = None
             if ev is not None:
                 ev.record()
         if not direct:
             ops.weight_unpack_grad(dwp, g, self._cmap(name), L["cout"], L["cin"], L["taps"], L["cin_p"], False)
-        if bias is not None:
-            ops.col_sum(dy, self.pg[bias], L["cout"])
+        if db is not None:
+            ops.col_sum(dy, db, L["cout"])
 
     def gn_fwd(self, x, prefix, G, want_xbar=False):
         B, N, C = ops._bnc(x)

@@ -94,8 +94,11 @@ def conv_fwd(desc, x, w, bias, y, use_tc=False, gn_sums=None):
         K.crd_conv_fwd(ctypes.byref(desc), P(x), P(w), P(bias), P(y), stream())
 
 
-def conv_wgrad(desc, x, dy, dw, use_tc=False):
-    if use_tc:
+def conv_wgrad(desc, x, dy, dw, use_tc=False, db=None):
+    """db (tensor-core 1x1 path only): the bias gradient is accumulated by the same kernel."""
+    if use_tc and db is not None:
+        K.crd_conv_wgrad_bias_tc(ctypes.byref(desc), P(x), P(dy), P(dw), P(db), stream())
+    elif use_tc:
         K.crd_conv_wgrad_tc(ctypes.byref(desc), P(x), P(dy), P(dw), stream())
     else:
         K.crd_conv_wgrad(ctypes.byref(desc), P(x), P(dy), P(dw), stream())

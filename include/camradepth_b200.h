@@ -84,6 +84,10 @@ CRD_API int crd_conv_wgrad(const crd_conv_desc* d, const void* x, const void* dy
 CRD_API int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                     float* gn_sums, crd_stream_t stream);
 CRD_API int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const void* dy, float* dw, crd_stream_t stream);
+/* 1x1 contractions with a bias (encoder q / k / fc1 / fc2 Conv1d, simplified_attention.py:16-21,66-67): the weight
+ * gradient and the bias gradient db[co] += sum_pixels dY from one pass over dY (an extra MMA against ones). */
+CRD_API int crd_conv_wgrad_bias_tc(const crd_conv_desc* d, const void* x, const void* dy, float* dw, float* db,
+                           crd_stream_t stream);
 
 /* weight repacking between the reference's parameter layout and the kernels' K-major layout.
  * mode 0 (fwd):   dst[co][tap][map[ci]] = w[co][ci][tap]            dst is [Cout][KH*KW][Cin_p]

@@ -91,6 +91,13 @@ def test_conv_tc_fwd_and_dgrad(case):
     if cin_p > Cin:      # padded input channels must receive exactly zero
         pad_cols = dwp.view(Cout, k * k, cin_p)[:, :, Cin:]
         assert float(pad_cols.abs().max()) == 0
+    if k == 1:
+        # 1x1: weight and bias gradients from one pass over dy (an extra MMA against a tile of ones), accumulating
+        dwp2 = torch.zeros_like(dwp)
+        db = torch.full((Cout,), 0.5, dtype=torch.float32, device=d)
+        ops.conv_wgrad(ops.make_desc(xb, dys, cin_p, Cout, k, k, 1, pad), xb, dys, dwp2, use_tc=True, db=db)
+        assert rel(dwp2, dwp) < 1e-5
+        assert rel(db - 0.5, rnd(gy, BF).sum((0, 2, 3))) < 1e-4
 
 
 def test_conv_tc_large_matches_simt():
