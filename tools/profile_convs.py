@@ -45,3 +45,15 @@ tot = sum(v[0] for v in agg.values())
 print(f"B={B}: conv launches total {tot:.2f} ms")
 for (kind, g), (ms, n, _) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:60]:
     print(f"{ms:8.3f} ms {n:4d}  {kind:6s} {g}")
+
+# decoder layers one by one, with the useful tensor throughput (2 * pixels * Cout * Cin * taps per launch)
+print("\ndecoder convolutions, per layer:")
+for (kind, name), evs in sorted(eng.timed.items(), key=lambda kv: kv[0][1]):
+    if "depth_upsample" not in name or not evs:
+        continue
+    L = eng.L[name]
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    st = int(name.split(".")[1])
+    px = B * (12 * 26) * 4 ** st
+    fl = 2.0 * px * L["cout"] * L["cin"] * L["taps"]
+    print(f"{ms:8.3f} ms x{len(evs)}  {kind:6s} {name:52s} Cin {L['cin']:4d} Cout {L['cout']:4d}  {fl / ms / 1e9:7.0f} TF/s useful")
