@@ -61,3 +61,30 @@ class GraphedTrainStep:
                 self.static[k].copy_(v, non_blocking=True)
         self.graph.replay()
         return self.loss
+
+    # ---- double-buffered input feed: the host->device copy of the NEXT batch runs on a copy stream while the
+    # graph of the current step executes; the step itself starts with a device-to-device copy into the static
+    # inputs (the reference hides its H2D copies behind DataLoader workers + .to(device), runner.py:176-190)
+    def prefetch(self, host_batch):
+        """Start copying a (pinned) host batch to the device; returns immediately."""
+        if not hasattr(self, "_stage"):
+            self._stage = {k: torch.empty_like(v) for k, v in self.static.items()}
+            self._copy_stream = torch.cuda.Stream()
+            self._staged = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record()
+        self._copy_stream.wait_event(self._consumed)          # the previous staging contents have been taken
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in host_batch.items():
+                self._stage[k].copy_(v, non_blocking=True)
+            self._staged.record()
+
+    def run_prefetched(self):
+        """Run one step on the batch passed to the last prefetch()."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        for k, v in self._stage.items():
+            self.static[k].copy_(v, non_blocking=True)
+        self._consumed.record()
+        self.graph.replay()
+        return self.loss

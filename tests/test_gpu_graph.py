@@ -52,6 +52,39 @@ def test_graphed_train_step_matches_eager():
     assert o1.state[next(iter(m1.parameters()))]["step"] == o2.state[next(iter(m2.parameters()))]["step"]
 
 
+def test_graphed_step_double_buffered_feed():
+    """prefetch() / run_prefetched(): the batch copied on the copy stream is the one the replay consumes."""
+    from camradepth_b200.graphs import GraphedTrainStep
+    from camradepth_b200.synthetic import make_batch
+    m, o, step, b = _setup(2)
+    for _ in range(2):
+        step(b)
+    g = GraphedTrainStep(step, b, warmup=0)
+    B, H, W = b["image"].shape[0], b["image"].shape[2], b["image"].shape[3]
+    hosts = [make_batch(B, H, W, seed=50 + i, pin=True) for i in range(3)]
+    hosts = [{k: h[k] for k in b} for h in hosts]
+    # reference losses: the same batches fed synchronously to an identical model/optimizer pair
+    m2, o2, step2, _ = _setup(2)
+    for _ in range(2):
+        step2(b)
+    g2 = GraphedTrainStep(step2, b, warmup=0)
+    want = []
+    for h in hosts:
+        o2.advance_for_replay()
+        want.append(float(g2({k: v.cuda() for k, v in h.items()})))
+    got = []
+    g.prefetch(hosts[0])
+    for i in range(3):
+        o.advance_for_replay()
+        loss = g.run_prefetched()
+        if i + 1 < 3:
+            g.prefetch(hosts[i + 1])
+        got.append(float(loss))
+    for a, c in zip(want, got):
+        assert abs(a - c) < 2e-2 * abs(a), (want, got)
+    assert abs(got[0] - got[1]) > 1e-6               # different batches really arrive
+
+
 def test_graphed_inference_matches_eager():
     from camradepth_b200.graphs import GraphedInference
     m, _, _, b = _setup(1)
