@@ -261,19 +261,22 @@ def main():
         with torch.cuda.graph(g_opt):
             opt_step()
 
-        def _replay(batch):
+        def _replay(prefetched):
             opt.advance_for_replay()
-            loss = g_fb(batch)
+            loss = g_fb.run_prefetched() if prefetched else g_fb(None)
             dist.all_reduce(eng._flat_own, op=dist.ReduceOp.AVG)
             g_opt.replay()
             return loss
 
         def run_resident():
-            return _replay(None)
+            return _replay(False)
 
         def run_e2e():
-            loss = _replay(host)
+            loss = _replay(True)                     # same double-buffered feed as the single-GPU arm
+            g_fb.prefetch(host)
             loss_host.copy_(loss.detach().view(1), non_blocking=True)
+
+        g_fb.prefetch(host)
     else:
         def run_resident():
             return step(devb)
@@ -344,7 +347,7 @@ def main():
                        if use_graph else "eager kernel launches",
                        "e2e_feed": ("pinned host batch -> device staging buffers on a copy stream, overlapped with the "
                                     "previous step; D2D into the graph's static inputs; D2H loss read every step"
-                                    if (use_graph and world == 1) else "H2D copies on the compute stream every step"),
+                                    if use_graph else "H2D copies on the compute stream every step"),
                        "l2": "no flush: per-step working set (several GB of activations) is far larger than the 126 MB L2",
                        "step_flops": FLOPS_TRAIN_PER_SAMPLE.get(a.variant, 0) * B,
                        "step_tensor_frac_of_" + pk_src: (value / world) * FLOPS_TRAIN_PER_SAMPLE.get(a.variant, 0) / 1e12 / peak},

@@ -977,6 +977,7 @@ namespace {
 // out-of-bounds fill zeroes the channels between hd and the next multiple of 16 (hd = 40) and the keys >= M.
 struct QkParams {
   int N, M, heads, hd, ksteps, bn, bufcols;
+  int nch;                  // key chunks of bn (<= 256) keys per head; items = heads * nch
   float scale;
 };
 constexpr int QK_A_BYTES = 128 * 128;            // 128 tokens x 64 channels bf16
@@ -994,6 +995,7 @@ qkmax_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, n0 = blockIdx.x * 128;
+  const int items = p.heads * p.nch;              // (head, key chunk) pairs, pipelined over two stages
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; i++) {
@@ -1015,22 +1017,24 @@ qkmax_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int h = 0; h < p.heads; h++) {
-        const int st = h & 1;
-        mbar_wait(bar_empty + 8 * st, ((h >> 1) & 1) ^ 1);
+      int h = 0, ch = 0;
+      for (int it = 0; it < items; it++) {
+        const int st = it & 1;
+        mbar_wait(bar_empty + 8 * st, ((it >> 1) & 1) ^ 1);
         const uint32_t sa = base + st * stage_bytes, bar = bar_full + 8 * st;
         mbar_expect_tx(bar, QK_A_BYTES + b_bytes);
         tma_load_3d(sa, &map_q, bar, h * p.hd, n0, b);
-        tma_load_4d(sa + QK_A_BYTES, &map_k, bar, 0, h, 0, b);
+        tma_load_4d(sa + QK_A_BYTES, &map_k, bar, 0, h, ch * p.bn, b);
+        if (++ch == p.nch) { ch = 0; ++h; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, p.bn);
-      for (int h = 0; h < p.heads; h++) {
-        const int st = h & 1;
-        mbar_wait(bar_tempty + 8 * st, ((h >> 1) & 1) ^ 1);        // accumulator buffer drained
-        mbar_wait(bar_full + 8 * st, (h >> 1) & 1);
+      for (int it = 0; it < items; it++) {
+        const int st = it & 1;
+        mbar_wait(bar_tempty + 8 * st, ((it >> 1) & 1) ^ 1);        // accumulator buffer drained
+        mbar_wait(bar_full + 8 * st, (it >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = base + st * stage_bytes, sb = sa + QK_A_BYTES;
         for (int kk = 0; kk < p.ksteps; kk++)
@@ -1044,13 +1048,16 @@ qkmax_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int lg = warp & 3;
     const int n = n0 + lg * 32 + lane;
     float total = 0.f;
-    for (int h = 0; h < p.heads; h++) {
-      const int st = h & 1;
-      mbar_wait(bar_tfull + 8 * st, (h >> 1) & 1);
+    float best = -INFINITY;
+    int besti = 0;
+    int h = 0, ch = 0;
+    for (int it = 0; it < items; it++) {
+      const int st = it & 1;
+      mbar_wait(bar_tfull + 8 * st, (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(st * p.bufcols);
-      float best = -INFINITY;
-      int besti = 0;
+      const int m0 = ch * p.bn;
+      const int mval = min(p.bn, p.M - m0);                        // keys of this chunk that exist
       for (int c = 0; c < p.bn; c += 16) {
         uint32_t r[16];
         tmem_ld16(taddr + (uint32_t)c, r);
@@ -1058,14 +1065,17 @@ qkmax_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 16; j++) {
           const float v = __uint_as_float(r[j]);
-          if (c + j < p.M && v > best) { best = v; besti = c + j; }      // first occurrence wins ties
+          if (c + j < mval && v > best) { best = v; besti = m0 + c + j; }   // first occurrence wins ties
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * st);
-      total += best;
-      if (n < p.N) idx[((long long)b * p.heads + h) * p.N + n] = (unsigned short)besti;
+      if (++ch == p.nch) {
+        total += best;
+        if (n < p.N) idx[((long long)b * p.heads + h) * p.N + n] = (unsigned short)besti;
+        best = -INFINITY; besti = 0; ch = 0; ++h;
+      }
     }
     if (n < p.N) s_out[(long long)b * p.N + n] = total * p.scale;
   }
@@ -1083,12 +1093,13 @@ extern "C" int crd_attn_qkmax_fwd_tc(const void* q, const void* k, float* s, uns
                                      int C, int heads, float scale, crd_stream_t stream) {
   CRD_REQUIRE(q && k && s && idx && heads > 0 && C % heads == 0);
   const int hd = C / heads;
-  if (hd % 8 || hd > 64 || M > 256 || M < 1 || C % 8 || N < 1 || B < 1) return 1;
+  if (hd % 8 || hd > 64 || M > 65535 || M < 1 || C % 8 || N < 1 || B < 1) return 1;
   if (((uintptr_t)q & 15) || ((uintptr_t)k & 15)) return 1;
   QkParams p;
   p.N = N; p.M = M; p.heads = heads; p.hd = hd;
   p.ksteps = (hd + 15) / 16;
-  p.bn = (M + 15) / 16 * 16;
+  p.bn = M > 256 ? 256 : (M + 15) / 16 * 16;       // more than 256 keys: chunks of 256 with a running max
+  p.nch = (M + p.bn - 1) / p.bn;
   p.bufcols = p.bn <= 32 ? 32 : (p.bn <= 64 ? 64 : (p.bn <= 128 ? 128 : 256));
   p.scale = scale;
   const int smem = 2 * (QK_A_BYTES + ((p.bn * 128 + 1023) & ~1023)) + 1024 + 128;

@@ -153,7 +153,8 @@ CRD_API int crd_dwconv3x3_bwd_weight(const void* dy, int dtype, const void* x, c
  * s[b,n] = scale * sum_h max_m q_h[b,n,:].k_h[b,m,:] ; idx = argmax key per head */
 CRD_API int crd_attn_qkmax_fwd(const void* q, const void* k, int dtype, float* s, unsigned short* idx, int B, int N,
                        int M, int C, int heads, float scale, crd_stream_t stream);
-/* tcgen05 variant of the score (bf16 q/k, head_dim <= 64 and a multiple of 8, M <= 256): per head one
+/* tcgen05 variant of the score (bf16 q/k, head_dim <= 64 and a multiple of 8; more than 256 keys run as chunks
+ * of 256 with a running max): per head one
  * Q_h K_h^T GEMM into tensor memory, max/argmax taken in the accumulator read-out (simplified_attention.py:96-105).
  * Returns 1 (nothing launched) when the shape is not covered; crd_attn_qkmax_fwd dispatches to it. */
 CRD_API int crd_attn_qkmax_fwd_tc(const void* q, const void* k, float* s, unsigned short* idx, int B, int N, int M,

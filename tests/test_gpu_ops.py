@@ -244,9 +244,9 @@ def test_dwconv(shape, dtype):
 
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("cfg", [(2, 200, 78, 64, 1), (2, 130, 70, 160, 4), (1, 78, 78, 256, 8), (2, 64, 4, 128, 2),
-                                 # several 128-token tiles; 200 keys (two 256-column accumulators); 300 keys (> 256:
-                                 # CUDA-core fallback of the bf16 path)
-                                 (3, 1300, 78, 128, 2), (2, 500, 200, 160, 4), (1, 300, 300, 64, 2)])
+                                 # several 128-token tiles; 200 keys (two 256-column accumulators); 300 and 1400
+                                 # keys (> 256: chunks of 256 keys with a running max)
+                                 (3, 1300, 78, 128, 2), (2, 500, 200, 160, 4), (1, 300, 300, 64, 2), (1, 2000, 1400, 128, 2)])
 def test_attention_score(cfg, dtype):
     from camradepth_b200 import ops
     B, N, M, C, heads = cfg
