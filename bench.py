@@ -334,7 +334,7 @@ def main():
         dom_ms = sum(dom) / max(1, len(dom))
         dom_tflops = DOMINANT_FLOPS_PER_SAMPLE * B / (dom_ms * 1e-3) / 1e12 if dom else None
         peak = pk["bf16_tflops_sustained"]
-        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        h2d = world * sum(v.numel() * v.element_size() for v in host.values())      # whole job, like `value`
         out = {
             "metric": "train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -351,7 +351,7 @@ def main():
                        "l2": "no flush: per-step working set (several GB of activations) is far larger than the 126 MB L2",
                        "step_flops": FLOPS_TRAIN_PER_SAMPLE.get(a.variant, 0) * B,
                        "step_tensor_frac_of_" + pk_src: (value / world) * FLOPS_TRAIN_PER_SAMPLE.get(a.variant, 0) / 1e12 / peak},
-            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "kernel": "conv_tc_halo_kernel: tcgen05 implicit-GEMM 3x3 conv fwd, depth_upsample[4] layer 2 "
