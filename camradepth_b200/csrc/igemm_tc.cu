@@ -620,9 +620,18 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
   }
   const int gx = p.flat ? crd_div_up(P, TC_BM) : p.tiles_w * p.tiles_h * d->B;
   // N tiles of equal width <= 256 (one pass over A per tile; rows past Cout are zero-filled by TMA)
-  const int ntile = (d->Cout + 255) / 256;
+  int ntile = (d->Cout + 255) / 256;
+  {
+    // small problems (fewer CTAs than two per SM) are latency-bound by the serial accumulator read-out of one
+    // wide tile: narrower N tiles (>= 32 columns) spread it over the idle SMs; A is re-read from L2, which is
+    // free at these sizes
+    const int want = (2 * sm_count() + gx - 1) / gx, most = (d->Cout + 31) / 32;
+    if (want > ntile) ntile = want < most ? want : most;
+    if (ntile < 1) ntile = 1;
+  }
   p.bn = ((d->Cout + ntile - 1) / ntile + 15) / 16 * 16;
-  p.tmem_cols = p.bn <= 128 ? 128 : 256;
+  ntile = (d->Cout + p.bn - 1) / p.bn;
+  p.tmem_cols = p.bn <= 32 ? 32 : (p.bn <= 64 ? 64 : (p.bn <= 128 ? 128 : 256));
   p.stage_bytes = TC_A_BYTES + p.bn * TC_BK * 2;
   p.nstages = TC_SMEM_BUDGET / p.stage_bytes;
   if (p.nstages > TC_MAX_STAGES) p.nstages = TC_MAX_STAGES;
