@@ -668,6 +668,7 @@ struct WgParams {
   int Cin, Cout, kchunks;
   int mblocks;              // 64-channel blocks of dY in this launch (1 or 2)
   int halo;                 // 3x3: one X box with TH+2 rows per (chunk, kw); the kh taps are its 2-KiB row offsets
+  int cpc;                  // 1x1: 64-channel chunks of X per CTA (3, or fewer when the launch would not fill the GPU)
   int bias;                 // 1x1 only: also produce db[co] = sum_px dY (an extra N=64 MMA against a tile of ones)
   long long Ktot;           // row stride of dw
 };
@@ -712,8 +713,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     c0 = chunk * 64;
     nblk = p.KW;
   } else {
-    c0 = blockIdx.x * 192;
-    nblk = min(3, p.kchunks - (int)blockIdx.x * 3);
+    c0 = blockIdx.x * 64 * p.cpc;
+    nblk = min(p.cpc, p.kchunks - (int)blockIdx.x * p.cpc);
   }
   const int co0 = blockIdx.z * 128;
   const int mblocks = min(p.mblocks, (p.Cout - co0 + 63) / 64);
@@ -924,7 +925,14 @@ static int conv_wgrad_tc_impl(const crd_conv_desc* d, const void* x, const void*
     rc = make_map(&map_x, x, 4, dims2, str2, boxx);
   }
   if (rc) return rc;
-  const int gy = p.flat ? (p.kchunks + 2) / 3 : p.kchunks * p.KH;
+  p.cpc = 3;
+  if (p.flat) {
+    // small 1x1 problems: one or two chunks per CTA instead of three, so that the serial accumulator read-out
+    // (16 columns per round trip) is spread over more of the idle SMs
+    const long long gz0 = (d->Cout + 127) / 128, sms0 = sm_count();
+    while (p.cpc > 1 && ((p.kchunks + p.cpc - 1) / p.cpc) * gz0 * ((p.total_tiles + 3) / 4) < sms0) p.cpc--;
+  }
+  const int gy = p.flat ? (p.kchunks + p.cpc - 1) / p.cpc : p.kchunks * p.KH;
   const int gz = (d->Cout + 127) / 128;
   // Split-K over the pixel tiles.  One CTA per SM is resident (200 KB ring), so the launch runs in waves of
   // sm_count CTAs: pick the split count minimising waves * (tiles per CTA + fixed prologue/epilogue cost, in
