@@ -225,10 +225,10 @@ def main():
     use_graph = not a.no_graph
     for _ in range(a.warmup):
         step(devb)
-    eng = model._engines[a.precision]
     n0 = ops.launch_count()
     step(devb)
     launches_per_step = ops.launch_count() - n0
+    eng = model._engines[a.precision]
     if use_graph and world == 1:
         # the whole step (fwd + losses + bwd + optimizer) is captured once and replayed; the optimizer's
         # host-side bookkeeping (step counters, device-resident step size) runs before each replay
