@@ -79,6 +79,10 @@ class GraphedTrainStep:
                 self._stage[k].copy_(v, non_blocking=True)
             self._staged.record()
 
+    def wait_prefetch(self):
+        """Make the current stream wait for the copy started by the last prefetch()."""
+        torch.cuda.current_stream().wait_event(self._staged)
+
     def run_prefetched(self):
         """Run one step on the batch passed to the last prefetch()."""
         cur = torch.cuda.current_stream()
