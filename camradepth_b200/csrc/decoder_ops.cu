@@ -138,24 +138,29 @@ __global__ void conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restr
     const int ww = (int)(pix % W);
     const int hh = (int)((pix / W) % H);
     const int b = (int)(pix / ((long long)W * H));
-    float acc = bias ? bias[0] : 0.f;
-    for (int dh = -1; dh <= 1; dh++) {
-      const int h2 = hh + dh;
-      if (h2 < 0 || h2 >= H) continue;
-      for (int dw = -1; dw <= 1; dw++) {
-        const int w2 = ww + dw;
-        if (w2 < 0 || w2 >= W) continue;
-        const T* xp = x + (((long long)b * H + h2) * W + w2) * ldx;
-        const float* wp = ws + ((dh + 1) * 3 + (dw + 1)) * Cin;
-        for (int c = 0; c < Cin; c += 8) {
-          float v[8];
-          load8(xp + c, v);
+    // eight independent accumulators (one per lane of the 16-byte vector) instead of one 288-long FMA chain;
+    // clamped addresses + masks keep the nine taps branch-free
+    float acc[8];
 #pragma unroll
-          for (int j = 0; j < 8; j++) acc = fmaf(v[j], wp[c + j], acc);
-        }
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+      const int h2 = hh + t / 3 - 1, w2 = ww + t % 3 - 1;
+      const bool ok = (h2 >= 0) & (h2 < H) & (w2 >= 0) & (w2 < W);
+      const int hc = min(max(h2, 0), H - 1), wc = min(max(w2, 0), W - 1);
+      const T* xp = x + (((long long)b * H + hc) * W + wc) * ldx;
+      const float* wp = ws + t * Cin;
+      for (int c = 0; c < Cin; c += 8) {
+        float v[8];
+        load8(xp + c, v);
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = fmaf(ok ? v[j] : 0.f, wp[c + j], acc[j]);
       }
     }
-    y[pix] = acc;
+    float tot = bias ? bias[0] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) tot += acc[j];
+    y[pix] = tot;
   }
 }
 
@@ -204,25 +209,29 @@ __global__ void conv_c1_bwd_weight_kernel(const float* __restrict__ dy, const T*
   for (int q = 0; q < 10; q++)
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[q][j] = 0.f;
+  // dw[tap] = sum_p dy[p] x[p + tap] = sum_q x[q] dy[q - tap]: ONE 16-byte load of x per pixel, the nine dy scalars
+  // (1 channel, fp32) come from L1; clamped addresses + masks keep the loop branch-free
+  const float* dyb = dy + (long long)b * N;
+  const T* xb = x + (long long)b * N * ldx + cv * 8;
   for (long long p = p0 + ry; p < p1; p += rows) {
     const int hh = (int)(p / W), ww = (int)(p % W);
-    const float g = dy[(long long)b * N + p];
-    acc[9][0] += g;
+    const typename Raw8<T>::type raw = ldg16(xb + p * ldx);
+    float g[9];
 #pragma unroll
-    for (int dh = -1; dh <= 1; dh++) {
-      const int h2 = hh + dh;
-      if (h2 < 0 || h2 >= H) continue;
-#pragma unroll
-      for (int dw_ = -1; dw_ <= 1; dw_++) {
-        const int w2 = ww + dw_;
-        if (w2 < 0 || w2 >= W) continue;
-        float v[8];
-        load8(x + (((long long)b * H + h2) * W + w2) * ldx + cv * 8, v);
-        const int tap = (dh + 1) * 3 + (dw_ + 1);
-#pragma unroll
-        for (int j = 0; j < 8; j++) acc[tap][j] = fmaf(g, v[j], acc[tap][j]);
-      }
+    for (int t = 0; t < 9; t++) {
+      const int h2 = hh - (t / 3 - 1), w2 = ww - (t % 3 - 1);
+      const bool ok = (h2 >= 0) & (h2 < H) & (w2 >= 0) & (w2 < W);
+      const int hc = min(max(h2, 0), H - 1), wc = min(max(w2, 0), W - 1);
+      const float gv = dyb[(long long)hc * W + wc];
+      g[t] = ok ? gv : 0.f;
     }
+    float v[8];
+    unpack8(raw, v);
+    if (cv == 0) acc[9][0] += g[4];
+#pragma unroll
+    for (int t = 0; t < 9; t++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[t][j] = fmaf(g[t], v[j], acc[t][j]);
   }
 #pragma unroll
   for (int q = 0; q < 10; q++) {
