@@ -167,6 +167,13 @@ class Engine:
     def _empty(self, *shape, dtype=None):
         return torch.empty(*shape, dtype=self.tdtype if dtype is None else dtype, device=self.device)
 
+    def _feat(self, B, H, W, FW):
+        """Feature buffer [feat 128 | depth | seg maps | pad]: the 128 feature channels are fully written by the
+        decoder block, so only the tail channels are zero-filled (a full fill of the 192x416 buffer is 0.7 GB)."""
+        t = self._empty(B, H, W, FW)
+        t[..., MID:].zero_()
+        return t
+
     def _zeros(self, *shape, dtype=None):
         return torch.zeros(*shape, dtype=self.tdtype if dtype is None else dtype, device=self.device)
 
@@ -720,17 +727,17 @@ class Engine:
         F2 = self._empty(B, 4 * h0, 4 * w0, MID)
         S["D1"] = self.dec_fwd("depth_upsample.1", F1, skip_from(3, stage_T[1], MID), F2, d2[1], save)
         FW = r8(MID + 1 + cfg.nseg)                    # [feat 128 | depth | seg maps | zero pad]
-        F3 = self._zeros(B, 8 * h0, 8 * w0, FW)
+        F3 = self._feat(B, 8 * h0, 8 * w0, FW)
         S["D2"] = self.dec_fwd("depth_upsample.2", F2, skip_from(4, stage_T[0], MID), F3[..., :MID], d2[2], save)
         S["fe"] = fe
         inter3, S["DA3"] = self.da_fwd("depth_activation_3", F3, save)
         ops.nchw_to_nhwc(inter3, F3[..., MID:MID + 1])
-        F4 = self._zeros(B, 16 * h0, 16 * w0, FW)
+        F4 = self._feat(B, 16 * h0, 16 * w0, FW)
         S["D3"] = self.dec_fwd("depth_upsample.3", F3, None, F4[..., :MID], d2[3], save)
         seg = cfg.sup or cfg.unsup
         FS4 = None
         if seg:
-            FS4 = self._zeros(B, 16 * h0, 16 * w0, FW)
+            FS4 = self._feat(B, 16 * h0, 16 * w0, FW)
             S["S0"] = self.dec_fwd("seg_upsample.0", F3, None, FS4[..., :MID], d2[4], save)
             if cfg.sup:
                 lg = self.seg_logits(FS4, "seg_conv_stage_4", self.tdtype)
@@ -748,7 +755,7 @@ class Engine:
         def skip_input(cat):
             ops.nchw_to_nhwc(x, cat[..., MID + 1:MID + 1 + cin])
 
-        F5 = self._zeros(B, H, W, FW)
+        F5 = self._feat(B, H, W, FW)
         S["D4"] = self.dec_fwd("depth_upsample.4", F4, skip_input, F5[..., :MID], d2[5 if seg else 4], save)
         final_seg = unsup_map = None
         if seg:
@@ -819,7 +826,10 @@ class Engine:
             return g.detach().contiguous().float()
 
         # ---- heads at full resolution
-        dF5 = self._zeros(B, H, W, FW)
+        # the depth head's data gradient (accumulate=False) overwrites every channel it reads; a zero fill is only
+        # needed when the buffer is wider than that
+        da5_w = self.L["depth_activation_5.conv_1.weight"]["cin_p"]
+        dF5 = self._empty(B, H, W, FW) if da5_w == FW else self._zeros(B, H, W, FW)
         self.da_bwd("depth_activation_5", S["DA5"], gz(g_final, (B, 1, H, W)), dF5, False)
         sup_grad = cfg.sup and g_seg is not None
         dFS4 = None
