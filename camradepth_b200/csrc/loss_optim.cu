@@ -64,7 +64,9 @@ __global__ void ce_fwd_kernel(const float* __restrict__ logits, const long long*
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long t = target[i];
-    if (t != ignore_index) {
+    // labels outside [0, C) other than ignore_index make F.cross_entropy raise in the reference; here they are
+    // treated like ignored pixels instead of indexing out of bounds
+    if (t != ignore_index && t >= 0 && t < C) {
       const long long b = i / HW, r = i - b * HW;
       const float* lp = logits + b * C * HW + r;
       float m = -INFINITY;
@@ -99,7 +101,7 @@ __global__ void ce_bwd_kernel(const float* __restrict__ logits, const long long*
     const long long b = i / HW, r = i - b * HW;
     const float* lp = logits + b * C * HW + r;
     float* dp = dlogits + b * C * HW + r;
-    if (t == ignore_index) {
+    if (t == ignore_index || t < 0 || t >= C) {
       for (int c = 0; c < C; c++) dp[c * HW] = 0.f;
       continue;
     }
@@ -172,10 +174,11 @@ __global__ void __launch_bounds__(256) diffgradnorm_kernel(const crd_opt_tensor*
 }
 
 // ------------------------------------------------------------------ test-mode metrics (runner.py:442-492)
-// pred is clipped to [0,1]; both are scaled by max_depth; valid = gt > 0 (and gt >= thr2 for the second set).
+// pred is clipped to [0,1]; both are scaled by max_depth; valid = 0 < gt <= thr1 (runner.py:455-457 zeroes
+// gt > max_distances[0] first), and additionally gt >= thr2 for the second set (:473-475).
 // acc[0..3] = (sum sq, sum abs, sum rel, count) within max range; acc[4..7] = same for gt >= thr2.
 __global__ void depth_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt, float* acc,
-                                     long long n, float max_depth, float thr2) {
+                                     long long n, float max_depth, float thr1, float thr2) {
   __shared__ float sh[32];
   float a[8];
 #pragma unroll
@@ -183,7 +186,7 @@ __global__ void depth_metrics_kernel(const float* __restrict__ pred, const float
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const float g = gt[i] * max_depth;
-    if (g > 0.f) {
+    if (g > 0.f && !(g > thr1)) {
       const float p = fminf(fmaxf(pred[i], 0.f), 1.f) * max_depth;
       const float e = p - g, ae = fabsf(e), re = ae / g;
       a[0] = fmaf(e, e, a[0]); a[1] += ae; a[2] += re; a[3] += 1.f;
@@ -329,11 +332,11 @@ extern "C" int crd_diffgradnorm_update(const crd_opt_tensor* table, const crd_op
 }
 
 extern "C" int crd_depth_metrics(const float* pred, const float* gt, float* acc, float* out, long long n,
-                                 float max_depth, float thr2, crd_stream_t stream) {
+                                 float max_depth, float thr1, float thr2, crd_stream_t stream) {
   if (n == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(acc, 0, 8 * sizeof(float), s);
-  depth_metrics_kernel<<<red_blocks(n), 256, 0, s>>>(pred, gt, acc, n, max_depth, thr2);
+  depth_metrics_kernel<<<red_blocks(n), 256, 0, s>>>(pred, gt, acc, n, max_depth, thr1, thr2);
   CRD_LAUNCH_CHECK();
   depth_metrics_finalize_kernel<<<1, 1, 0, s>>>(acc, out);
   CRD_LAUNCH_CHECK();

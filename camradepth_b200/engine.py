@@ -347,13 +347,16 @@ class Engine:
         cfg = self.cfg
         nb = sum(cfg.depths)
         rates = torch.linspace(0, DROP_PATH_RATE, nb).tolist()     # simplified_attention.py:214
+        # Block.forward calls self.drop_path twice (:143-144) and timm's drop_path draws an independent per-sample
+        # mask per call: two scales per block, in call order (attention branch, then Mix-FFN branch)
         dps = []
         for r in rates:
-            if r == 0.0:
-                dps.append(None)                                    # Identity (:123)
-            else:
-                keep = 1.0 - r
-                dps.append((torch.rand(B, device=self.device) < keep).float() / keep)
+            for _ in range(2):
+                if r == 0.0:
+                    dps.append(None)                                # Identity (:123)
+                else:
+                    keep = 1.0 - r
+                    dps.append((torch.rand(B, device=self.device) < keep).float() / keep)
         d2s = [(torch.rand(B, MID, device=self.device) >= DROPOUT2D_P).float() / (1 - DROPOUT2D_P)
                for _ in range(cfg.n_dropout_sites)]
         return dps, d2s
@@ -386,7 +389,7 @@ class Engine:
         if dxin is not None:
             self.conv_dgrad(dy, name + ".proj.weight", dxin, accumulate)
 
-    def block_fwd(self, s, i, x, dp, save):
+    def block_fwd(self, s, i, x, dp, dp_mlp, save):
         cfg = self.cfg
         p = f"dest_encoder.block{s + 1}.{i}"
         B, H, W, C = x.shape
@@ -441,12 +444,12 @@ class Engine:
         y2 = self._empty(B, H, W, C)
         self.conv(h3, p + ".mlp1.fc2.weight", y2, bias=p + ".mlp1.fc2.bias")
         x_out = self._empty(B, H, W, C, dtype=f32)
-        ops.residual_add(x_mid.view(B, N, C), y2.view(B, N, C), dp, x_out.view(B, N, C))
+        ops.residual_add(x_mid.view(B, N, C), y2.view(B, N, C), dp_mlp, x_out.view(B, N, C))
         if not save:
             return x_out, None
         rec.update(x=x, ab1=ab1, mr1=mr1, xbar1=xbar1, x1=x1, q=q, k=k, sc=sc, idx=idx, pv=pv, x_mid=x_mid,
                    ab2=ab2, mr2=mr2, x2=x2, h1=h1, ab_m1=ab_m1, mr_m1=mr_m1, h2=h2, ab_m2=ab_m2, mr_m2=mr_m2,
-                   h3=h3, dp=dp, M=M, scale=scale)
+                   h3=h3, dp=dp, dp_mlp=dp_mlp, M=M, scale=scale)
         return x_out, rec
 
     def block_bwd(self, s, i, rec, dx):
@@ -462,7 +465,7 @@ class Engine:
         dp = rec["dp"]
         # ---- Mix-FFN branch
         dy2 = self._empty(B, H, W, C)
-        ops.scale_cast(dx, dp, dy2)
+        ops.scale_cast(dx, rec["dp_mlp"], dy2)
         self.conv_wgrad(rec["h3"], dy2, p + ".mlp1.fc2.weight", bias=p + ".mlp1.fc2.bias")
         dh3 = self._empty(B, H, W, rC)
         self.conv_dgrad(dy2, p + ".mlp1.fc2.weight", dh3, False)
@@ -681,8 +684,11 @@ class Engine:
         self.fwd_arena.reset()
         if train:
             dps, d2s = masks if masks is not None else self.make_masks(B)
+            if len(dps) != 2 * sum(cfg.depths) or len(d2s) != cfg.n_dropout_sites:
+                raise RuntimeError(f"expected {2 * sum(cfg.depths)} DropPath scales (two per block: attention branch, "
+                                   f"Mix-FFN branch) and {cfg.n_dropout_sites} Dropout2d scales, got {len(dps)} / {len(d2s)}")
         else:
-            dps, d2s = [None] * sum(cfg.depths), [None] * cfg.n_dropout_sites
+            dps, d2s = [None] * (2 * sum(cfg.depths)), [None] * cfg.n_dropout_sites
         S = dict(B=B, H=H, W=W)
         f32 = torch.float32
 
@@ -697,9 +703,9 @@ class Engine:
             pe_recs.append(prec)
             brs = []
             for i in range(cfg.depths[s]):
-                dp = dps[bi]
-                dp = None if dp is None else dp.to(self.device, f32).contiguous()
-                xr, brec = self.block_fwd(s, i, xr, dp, save)
+                dp, dp_mlp = (None if m is None else m.to(self.device, f32).contiguous()
+                              for m in (dps[2 * bi], dps[2 * bi + 1]))
+                xr, brec = self.block_fwd(s, i, xr, dp, dp_mlp, save)
                 brs.append(brec)
                 bi += 1
             blk_recs.append(brs)

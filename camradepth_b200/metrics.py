@@ -2,7 +2,7 @@
 reductions: masked RMSE / MAE / REL within 100 m and within 50 m, and mean IoU of the segmentation logits.
 
 Reference semantics kept: prediction clipped to [0,1], both maps scaled by `max_depth`, valid pixels are
-`gt > 0`; the 50 m subset is taken in inverse-depth space (`gt >= 50` after scaling, runner.py:473-477).
+`0 < gt <= max_distances[0]` (runner.py:455-457); the 50 m subset is taken in inverse-depth space (`gt >= 50` after scaling, runner.py:473-477).
 The reference's IoU call constructs `torchmetrics.JaccardIndex(ignore_index=255)` inside a try/except that
 swallows the resulting ValueError (runner.py:433-439), i.e. it reports NaN; here IoU is the standard mean over
 the classes present in prediction or label, ignoring label 255.
@@ -25,7 +25,8 @@ def depth_metrics(pred_depth: torch.Tensor, gt_depth: torch.Tensor, max_depth: f
     assert p.numel() == g.numel()
     acc = torch.empty(8, dtype=torch.float32, device=p.device)
     out = torch.empty(6, dtype=torch.float32, device=p.device)
-    K.crd_depth_metrics(P(p), P(g), P(acc), P(out), p.numel(), float(max_depth), float(max_distances[1]), stream())
+    K.crd_depth_metrics(P(p), P(g), P(acc), P(out), p.numel(), float(max_depth), float(max_distances[0]),
+                        float(max_distances[1]), stream())
     d0, d1 = int(max_distances[0]), int(max_distances[1])
     return {f"rmse_{d0}": out[0], f"mae_{d0}": out[1], f"rel_{d0}": out[2],
             f"rmse_{d1}": out[3], f"mae_{d1}": out[4], f"rel_{d1}": out[5]}

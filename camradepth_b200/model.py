@@ -131,7 +131,9 @@ class CamRaDepth(nn.Module):
 
     def set_stochastic_masks(self, drop_path_scales, dropout2d_scales):
         """Inject the DropPath / Dropout2d scale tensors used by the NEXT training-mode forward
-        (parity tests share masks with the reference)."""
+        (parity tests share masks with the reference).  drop_path_scales: 2 * sum(depths) entries
+        ((B,) tensors or None), one per `drop_path` call in the reference's call order -- attention branch then
+        Mix-FFN branch of every block (simplified_attention.py:143-144)."""
         self._masks = (list(drop_path_scales), list(dropout2d_scales))
 
     def _pop_masks(self):
@@ -161,18 +163,18 @@ class CamRaDepth(nn.Module):
 
 
 def load_checkpoint_with_shape_match(model, checkpoint_dict):
-    """utils.py:352-370: strip 'module.', copy name+shape matches, keep fresh init otherwise."""
-    checkpoint = {k.replace('module.', ''): v for k, v in checkpoint_dict.items()}
-    model_state_dict = model.state_dict()
-    new_state_dict = {}
-    for key in model_state_dict.keys():
-        if key in checkpoint and checkpoint[key].shape == model_state_dict[key].shape:
-            new_state_dict[key] = checkpoint[key]
+    """Same contract as the reference loader (utils.py:352-370): `module.` prefixes of DataParallel checkpoints are
+    ignored, a tensor is taken from the checkpoint only when both its name and its shape match, everything else keeps
+    the model's current (freshly initialised) value and is reported on stdout."""
+    have = {name.replace('module.', ''): t for name, t in checkpoint_dict.items()}
+    current = model.state_dict()
+    merged = dict(current)
+    for name, cur in current.items():
+        src = have.get(name)
+        if src is None:
+            print(f"{args.hashtags_prefix} Key not in checkpoint: ", name)
+        elif src.shape != cur.shape:
+            print(f"{args.hashtags_prefix} Shape mismatch: ", name, src.shape, cur.shape)
         else:
-            if key not in checkpoint:
-                print(f"{args.hashtags_prefix} Key not in checkpoint: ", key)
-            else:
-                print(f"{args.hashtags_prefix} Shape mismatch: ", key, checkpoint[key].shape,
-                      model_state_dict[key].shape)
-            new_state_dict[key] = model_state_dict[key]
-    model.load_state_dict(new_state_dict, strict=True)
+            merged[name] = src
+    model.load_state_dict(merged, strict=True)

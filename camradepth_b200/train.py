@@ -26,9 +26,11 @@ class TrainStep:
         self.i = 0                              # micro-batch index within the epoch
         self.training_steps = 0
         self._stats = None
+        self._stats_n = 0                       # micro-batches accumulated into _stats since the last stats()
 
     def start_epoch(self):
         self.i = 0
+        self._stats, self._stats_n = None, 0
         self.optimizer.zero_grad()
 
     def loss(self, pred, batch):
@@ -52,6 +54,7 @@ class TrainStep:
             seg = parts["seg"].detach() if torch.is_tensor(parts["seg"]) else torch.zeros_like(rmse)
             s = torch.stack([parts["final"].detach(), parts["s4"].detach(), rmse, seg])
             self._stats = s if self._stats is None else self._stats + s
+            self._stats_n += 1
         loss.backward()
         last = self.batches_per_epoch is not None and (self.i + 1) == self.batches_per_epoch
         stepped = False
@@ -69,9 +72,8 @@ class TrainStep:
         """Means since the last call (ONE device->host read): depth_final, depth_stage4, RMSE [m], seg."""
         if self._stats is None:
             return None
-        n = max(1, self.i)
-        out = (self._stats / n).tolist()
-        self._stats = None
+        out = (self._stats / max(1, self._stats_n)).tolist()
+        self._stats, self._stats_n = None, 0
         return {"loss_depth_final": out[0], "loss_depth_stage_4": out[1], "RMSE": out[2], "loss_seg": out[3]}
 
 

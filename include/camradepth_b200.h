@@ -213,10 +213,11 @@ CRD_API int crd_ce_bwd(const float* logits, const long long* target, const float
 CRD_API int crd_loss_finalize(const float* acc, float* out, int kind, float gamma, crd_stream_t stream);
 
 /* ---------------------------------------------------------------- test-mode metrics (runner.py:442-492)
- * pred clipped to [0,1], both scaled by max_depth, valid = gt > 0; second set additionally gt >= thr2 (the
- * "<= 50 m" subset in inverse-depth space).  acc: 8 floats scratch, out[6] = RMSE, MAE, REL x 2. */
+ * pred clipped to [0,1], both scaled by max_depth, valid = 0 < gt <= thr1 (max_distances[0], runner.py:455-457);
+ * second set additionally gt >= thr2 (the "<= 50 m" subset in inverse-depth space, :473-475).
+ * acc: 8 floats scratch, out[6] = RMSE, MAE, REL x 2. */
 CRD_API int crd_depth_metrics(const float* pred, const float* gt, float* acc, float* out, long long n,
-                      float max_depth, float thr2, crd_stream_t stream);
+                      float max_depth, float thr1, float thr2, crd_stream_t stream);
 /* conf[t][p] += #pixels with label t (!= ignore_index) predicted as p = argmax_c logits (NCHW) -- IoU input */
 CRD_API int crd_confusion(const float* logits, const long long* target, float* conf, int B, int C, long long HW,
                   int ignore_index, crd_stream_t stream);

@@ -239,13 +239,15 @@ def mlp(sd, p, x, H, W, C):
     return F.conv1d(x, sd[p + ".fc2.weight"], sd[p + ".fc2.bias"])
 
 
-def block(sd, p, x_orig, H, W, C, heads, sr, dp_scale=None):
-    """Block.forward (simplified_attention.py:141-145). dp_scale: (B,) DropPath scale or None."""
-    def dp(t):
-        return t if dp_scale is None else t * dp_scale.view(-1, 1, 1).to(t.dtype)
+def block(sd, p, x_orig, H, W, C, heads, sr, dp_attn=None, dp_mlp=None):
+    """Block.forward (simplified_attention.py:141-145).  `self.drop_path` is called twice (:143,:144) and timm's
+    drop_path draws an independent per-sample Bernoulli mask on every call, so the two residual branches get
+    their own (B,) DropPath scales: dp_attn for the attention branch, dp_mlp for the Mix-FFN branch."""
+    def dp(t, sc):
+        return t if sc is None else t * sc.view(-1, 1, 1).to(t.dtype)
     x = _gn(x_orig, sd, p + ".norm1", C // GN_DIV)
-    x = x_orig + dp(attention_maxpool(sd, p + ".attn", x, H, W, heads, sr))
-    x = x + dp(mlp(sd, p + ".mlp1", _gn(x, sd, p + ".norm2", C // GN_DIV), H, W, C))
+    x = x_orig + dp(attention_maxpool(sd, p + ".attn", x, H, W, heads, sr), dp_attn)
+    x = x + dp(mlp(sd, p + ".mlp1", _gn(x, sd, p + ".norm2", C // GN_DIV), H, W, C), dp_mlp)
     return x
 
 
@@ -258,8 +260,10 @@ def encoder(sd, cfg: Cfg, x, drop_path_scales: Optional[Sequence] = None):
     for s in range(4):
         x, H, W = patch_embed(sd, f"dest_encoder.patch_embed{s + 1}", x, pe_k[s], pe_s[s])
         for i in range(cfg.depths[s]):
-            sc = None if drop_path_scales is None else drop_path_scales[bi]
-            x = block(sd, f"dest_encoder.block{s + 1}.{i}", x, H, W, cfg.dims[s], cfg.heads[s], cfg.sr[s], sc)
+            # two scales per block, in call order: attention branch, then Mix-FFN branch
+            sa = None if drop_path_scales is None else drop_path_scales[2 * bi]
+            sm = None if drop_path_scales is None else drop_path_scales[2 * bi + 1]
+            x = block(sd, f"dest_encoder.block{s + 1}.{i}", x, H, W, cfg.dims[s], cfg.heads[s], cfg.sr[s], sa, sm)
             bi += 1
         x = x.reshape(B, -1, H, W).contiguous()
         outs.append(x)
@@ -450,7 +454,8 @@ def n_dropout_sites(cfg: Cfg) -> int:
 
 
 def make_masks(cfg: Cfg, B: int, seed: int):
-    """Seeded DropPath scales (34 x (B,)) and Dropout2d scales (5 or 7 x (B,128)).
+    """Seeded DropPath scales (2 x 34 x (B,): one per `drop_path` CALL, attention branch then Mix-FFN branch of
+    each block, simplified_attention.py:143-144) and Dropout2d scales (5 or 7 x (B,128)).
 
     DropPath: timm drop_path, rate linspace(0, .1, sum(depths)) (simplified_attention.py:214);
     block 0 has rate 0 -> Identity (:123).  Dropout2d(0.2): whole (b, channel) planes (CamRaDepth.py:96).
@@ -461,7 +466,8 @@ def make_masks(cfg: Cfg, B: int, seed: int):
     dps = []
     for r in rates:
         keep = 1.0 - r
-        dps.append((torch.rand(B, generator=g) < keep).float() / keep)
+        for _ in range(2):
+            dps.append((torch.rand(B, generator=g) < keep).float() / keep)
     d2 = [(torch.rand(B, MID, generator=g) >= DROPOUT2D_P).float() / (1 - DROPOUT2D_P)
           for _ in range(n_dropout_sites(cfg))]
     return dps, d2

@@ -88,19 +88,13 @@ def worker(variant, B, H, W, train, out_path):
                 m = self.q.pop(0)
                 return t * m.view(*m.shape, *([1] * (t.dim() - m.dim())))
 
+        # timm's DropPath draws a fresh per-sample mask on EVERY call and Block.forward calls it twice
+        # (simplified_attention.py:143-144): the injected module pops one mask per call, in call order
         dq = list(dps)
         bi = 0
         for s in range(4):
             for blk in getattr(model.dest_encoder, f"block{s + 1}"):
-                class DP(nn.Module):
-                    def __init__(self, m):
-                        super().__init__()
-                        self.m = m
-                        self.calls = 0
-
-                    def forward(self, t):
-                        return t * self.m.view(-1, 1, 1)
-                blk.drop_path = DP(dq[bi])
+                blk.drop_path = Inject([dq[2 * bi], dq[2 * bi + 1]])
                 bi += 1
         model.dropout = Inject(list(d2s))
     else:

@@ -36,11 +36,10 @@ def test_graphed_train_step_matches_eager():
     l_eager = [float(step1(b)) for _ in range(3)]
     for _ in range(3):
         step2(b)
-    g = GraphedTrainStep(step2, b, warmup=0)       # capture records the step; it executes only on replay
+    g = GraphedTrainStep(step2, b, warmup=0, optimizer=o2)    # capture records the step; it executes only on replay
     l_graph = []
     for _ in range(3):
-        o2.advance_for_replay()
-        l_graph.append(float(g(b)))
+        l_graph.append(float(g(b)))          # the graphed step advances the optimizer's step count itself
     torch.cuda.synchronize()
     assert abs(l_eager[0] - l_graph[0]) < 2e-3 * abs(l_eager[0])
     assert l_graph[2] != l_graph[0]                  # parameters really move between replays
@@ -59,7 +58,7 @@ def test_graphed_step_double_buffered_feed():
     m, o, step, b = _setup(2)
     for _ in range(2):
         step(b)
-    g = GraphedTrainStep(step, b, warmup=0)
+    g = GraphedTrainStep(step, b, warmup=0, optimizer=o)
     B, H, W = b["image"].shape[0], b["image"].shape[2], b["image"].shape[3]
     hosts = [make_batch(B, H, W, seed=50 + i, pin=True) for i in range(3)]
     hosts = [{k: h[k] for k in b} for h in hosts]
@@ -67,15 +66,13 @@ def test_graphed_step_double_buffered_feed():
     m2, o2, step2, _ = _setup(2)
     for _ in range(2):
         step2(b)
-    g2 = GraphedTrainStep(step2, b, warmup=0)
+    g2 = GraphedTrainStep(step2, b, warmup=0, optimizer=o2)
     want = []
     for h in hosts:
-        o2.advance_for_replay()
         want.append(float(g2({k: v.cuda() for k, v in h.items()})))
     got = []
     g.prefetch(hosts[0])
     for i in range(3):
-        o.advance_for_replay()
         loss = g.run_prefetched()
         if i + 1 < 3:
             g.prefetch(hosts[i + 1])
@@ -95,3 +92,12 @@ def test_graphed_inference_matches_eager():
     assert rel(out, ref) < 5e-3
     out2 = g(b["image"] * 0.5)["depth"]["final_depth"]
     assert rel(out2, ref) > 1e-3
+    # weights changed after the capture: the replay refreshes its packed copies inside the graph and must follow
+    # the eager forward
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(1.05)
+        ref3 = m(b["image"])["depth"]["final_depth"].clone()
+    out3 = g(b["image"])["depth"]["final_depth"]
+    assert rel(out3, ref3) < 5e-3
+    assert rel(ref3, ref) > 1e-3

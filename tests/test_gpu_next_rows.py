@@ -31,6 +31,19 @@ def test_depth_metrics_match_reference_loop():
     ref.update({"mae_50": err.abs().mean(), "rmse_50": err.pow(2).mean().sqrt(), "rel_50": (err.abs() / g[idx]).mean()})
     for k, v in ref.items():
         assert abs(float(m[k]) - float(v)) < 1e-4 * max(1.0, abs(float(v))), k
+    # max_distances[0] below max_depth: pixels with gt > max_distances[0] are dropped from both sets (runner.py:455-457)
+    m = depth_metrics(pred, gt, max_depth=100.0, max_distances=(80, 50))
+    g = gt.squeeze() * 100
+    g = g.clone(); g[g > 80] = 0
+    idx = torch.where(g > 0)
+    err = p[idx] - g[idx]
+    ref = {"mae_80": err.abs().mean(), "rmse_80": err.pow(2).mean().sqrt(), "rel_80": (err.abs() / g[idx]).mean()}
+    g[g < 50] = 0
+    idx = torch.where(g > 0)
+    err = p[idx] - g[idx]
+    ref.update({"mae_50": err.abs().mean(), "rmse_50": err.pow(2).mean().sqrt(), "rel_50": (err.abs() / g[idx]).mean()})
+    for k, v in ref.items():
+        assert abs(float(m[k]) - float(v)) < 1e-4 * max(1.0, abs(float(v))), k
 
 
 def test_mean_iou():
