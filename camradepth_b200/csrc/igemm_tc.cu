@@ -42,6 +42,14 @@ struct TcParams {
   int nstages, stage_bytes; // smem ring geometry: stage = A (16 KB) + B (bn * 128 B)
   int tmem_cols;            // 128 or 256
   int ldy, out_f32, act, accumulate;
+  int gnN;                  // pixels per sample (flat mode: sample of a pixel = pix / gnN) for the GroupNorm sums
+  // fused conv + argmax (Seg_Block, utils.py:95-100): am_ncls > 0 -> nothing is written to y; the per-pixel
+  // argmax over the first am_ncls output channels, divided by am_ncls, goes to up to two bf16 NHWC channels
+  // (pixel strides am_ld0 / am_ld1) and / or an fp32 (B,1,H,W) map
+  int am_ncls, am_ld0, am_ld1;
+  bf16* am0;
+  bf16* am1;
+  float* amf;
 };
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14),
@@ -81,79 +89,203 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
 }
 
-// Drain one accumulator row (this thread's TMEM lane): bias / sigmoid / accumulate in registers, 16-byte stores.
-// All 32 lanes execute the tcgen05.ld (warp-collective) even when their pixel is outside the image.
-__device__ __forceinline__ void epilogue_rows(const TcParams& p, uint32_t taddr, int n0, bool ok, long long pix,
-                                              const float* __restrict__ bias, void* __restrict__ yv) {
+// GroupNorm statistics in the accumulator read-out (utils.py:223-228, simplified_attention.py:34-43: every conv /
+// 1x1 contraction on the path that is followed by a GroupNorm).  Each lane holds 16 output channels of ONE pixel
+// (fp32, bias added, before the bf16 rounding); the warp's 32 pixels are reduced with a transposing butterfly:
+// 32 values per lane (16 sums + 16 squares) -> after 5 exchange steps (16+8+4+2+1 = 31 shuffles) lane l holds the
+// warp total of value l, i.e. lanes 0..15 the channel sums and lanes 16..31 the channel sums of squares, which go
+// to gn[b][channel][2] with one fp32 atomic per lane.  `sb` is the lane's sample (flat 1x1 tiles may straddle two
+// samples: one pass per sample present in the warp), `valid` masks pixels outside the tensor.
+__device__ __forceinline__ void gn_accumulate16(const float (&v)[16], bool valid, int sb, int n, int Cout,
+                                                float* __restrict__ gn) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int bmin = __reduce_min_sync(full, valid ? sb : 0x7fffffff);
+  const int bmax = __reduce_max_sync(full, valid ? sb : -1);
+  const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2, u1 = lane & 1;
+  for (int b = bmin; b <= bmax; b++) {
+    const bool mine = valid && sb == b;
+    float a[32];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const float x = mine ? v[j] : 0.f;
+      a[j] = x;
+      a[16 + j] = x * x;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const float send = u16 ? a[i] : a[i + 16], keep = u16 ? a[i + 16] : a[i];
+      a[i] = keep + __shfl_xor_sync(full, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const float send = u8 ? a[i] : a[i + 8], keep = u8 ? a[i + 8] : a[i];
+      a[i] = keep + __shfl_xor_sync(full, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float send = u4 ? a[i] : a[i + 4], keep = u4 ? a[i + 4] : a[i];
+      a[i] = keep + __shfl_xor_sync(full, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const float send = u2 ? a[i] : a[i + 2], keep = u2 ? a[i + 2] : a[i];
+      a[i] = keep + __shfl_xor_sync(full, send, 2);
+    }
+    {
+      const float send = u1 ? a[0] : a[1], keep = u1 ? a[1] : a[0];
+      a[0] = keep + __shfl_xor_sync(full, send, 1);
+    }
+    const int ch = n + (lane & 15);
+    if (ch < Cout) atomicAdd(gn + ((long long)b * Cout + ch) * 2 + (lane >> 4), a[0]);
+  }
+}
+
+// Seg_Block read-out: the thread's accumulator row holds every class logit of its pixel, so the argmax is a register
+// loop over the fp32 accumulators (first maximum wins, like torch.argmax) and the logits never reach memory.
+__device__ __forceinline__ void epilogue_argmax(const TcParams& p, uint32_t taddr, bool ok, long long pix,
+                                                const float* __restrict__ bias) {
+  float best = -INFINITY;
+  int bi = 0;
   for (int c = 0; c < p.bn; c += 16) {
     uint32_t r[16];
     tmem_ld16(taddr + (uint32_t)c, r);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (!ok) continue;
-    const int n = n0 + c;
-    if (n >= p.Cout) continue;
-    float v[16];
+    if (c >= p.am_ncls) continue;
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-      v[j] = __uint_as_float(r[j]);
-      if (bias && n + j < p.Cout) v[j] += bias[n + j];
-      if (p.act == CRD_ACT_SIGMOID) v[j] = sigmoid_f(v[j]);
-    }
-    const int nvalid = min(16, (p.Cout - n + 7) / 8 * 8);     // output buffers are padded to 8 channels
-    if (p.out_f32) {
-      float* yp = reinterpret_cast<float*>(yv) + pix * p.ldy + n;
-      for (int j = 0; j < nvalid; j += 8) {
-        float o[8];
-        if (p.accumulate) { load8(yp + j, o); } else {
-#pragma unroll
-          for (int q = 0; q < 8; q++) o[q] = 0.f;
-        }
-#pragma unroll
-        for (int q = 0; q < 8; q++) o[q] += (n + j + q < p.Cout) ? v[j + q] : 0.f;
-        store8(yp + j, o);
+      if (c + j < p.am_ncls) {
+        const float v = __uint_as_float(r[j]) + (bias ? bias[c + j] : 0.f);
+        if (v > best) { best = v; bi = c + j; }
       }
-    } else {
-      bf16* yp = reinterpret_cast<bf16*>(yv) + pix * p.ldy + n;
-      if (nvalid == 16 && n + 16 <= p.Cout && ((reinterpret_cast<uintptr_t>(yp) & 31) == 0)) {
-        // 16 bf16 = one full 32-byte sector per thread: 256-bit accesses (LDG/STG.E.ENL2.256)
-        uint32_t o[8];
-        if (p.accumulate) {
-          asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                       : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7])
-                       : "l"(yp));
+    }
+  }
+  if (!ok) return;
+  const float m = (float)bi / (float)p.am_ncls;
+  if (p.am0) p.am0[pix * p.am_ld0] = __float2bfloat16_rn(m);
+  if (p.am1) p.am1[pix * p.am_ld1] = __float2bfloat16_rn(m);
+  if (p.amf) p.amf[pix] = m;
+}
+
+// One 16-column chunk of an accumulator row: bias / GroupNorm sums / sigmoid / accumulate in registers, then one
+// 32-byte (bf16) store per thread.  `bv` holds the chunk's 16 bias values (zeros without a bias).
+__device__ __forceinline__ void process_chunk(const TcParams& p, const uint32_t (&r)[16], const float (&bv)[16], int n,
+                                              bool ok, long long pix, void* __restrict__ yv, float* __restrict__ gn,
+                                              int sb) {
+  float v[16];
 #pragma unroll
-          for (int q = 0; q < 8; q++) {
-            const float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&o[q]));
-            v[2 * q] += f.x; v[2 * q + 1] += f.y;
-          }
-        }
+  for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]) + bv[j];
+  if (gn) gn_accumulate16(v, ok, sb, n, p.Cout, gn);      // warp-uniform branch, all lanes take part
+  if (!ok) return;
+  if (p.act == CRD_ACT_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) v[j] = sigmoid_f(v[j]);
+  }
+  const int nvalid = min(16, (p.Cout - n + 7) / 8 * 8);     // output buffers are padded to 8 channels
+  if (p.out_f32) {
+    float* yp = reinterpret_cast<float*>(yv) + pix * p.ldy + n;
+    for (int j = 0; j < nvalid; j += 8) {
+      float o[8];
+      if (p.accumulate) { load8(yp + j, o); } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) o[q] = 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; q++) o[q] += (n + j + q < p.Cout) ? v[j + q] : 0.f;
+      store8(yp + j, o);
+    }
+  } else {
+    bf16* yp = reinterpret_cast<bf16*>(yv) + pix * p.ldy + n;
+    if (nvalid == 16 && n + 16 <= p.Cout && ((reinterpret_cast<uintptr_t>(yp) & 31) == 0)) {
+      // 16 bf16 = one full 32-byte sector per thread: 256-bit accesses (LDG/STG.E.ENL2.256)
+      uint32_t o[8];
+      if (p.accumulate) {
+        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7])
+                     : "l"(yp));
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-          o[q] = *reinterpret_cast<uint32_t*>(&h);
+          const float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&o[q]));
+          v[2 * q] += f.x; v[2 * q + 1] += f.y;
         }
-        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                     ::"l"(yp), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
-                     : "memory");
-        continue;
       }
-      for (int j = 0; j < nvalid; j += 8) {
-        float o[8];
-        if (p.accumulate) { load8(yp + j, o); } else {
 #pragma unroll
-          for (int q = 0; q < 8; q++) o[q] = 0.f;
-        }
-#pragma unroll
-        for (int q = 0; q < 8; q++) o[q] += (n + j + q < p.Cout) ? v[j + q] : 0.f;
-        store8(yp + j, o);
+      for (int q = 0; q < 8; q++) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+        o[q] = *reinterpret_cast<uint32_t*>(&h);
       }
+      asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                   ::"l"(yp), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                   : "memory");
+      return;
+    }
+    for (int j = 0; j < nvalid; j += 8) {
+      float o[8];
+      if (p.accumulate) { load8(yp + j, o); } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) o[q] = 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; q++) o[q] += (n + j + q < p.Cout) ? v[j + q] : 0.f;
+      store8(yp + j, o);
+    }
+  }
+}
+
+// The chunk's bias values: four 16-byte loads issued BEFORE the accumulator load is waited for (a scalar load per
+// channel behind the wait cost 40 % of the 1x1 GEMMs with wide outputs).
+__device__ __forceinline__ void load_bias16(const float* __restrict__ bias, int n, int Cout, float (&bv)[16]) {
+  if (bias && n + 16 <= Cout && ((reinterpret_cast<uintptr_t>(bias + n) & 15) == 0)) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(bias + n) + q);
+      bv[4 * q] = t.x; bv[4 * q + 1] = t.y; bv[4 * q + 2] = t.z; bv[4 * q + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; j++) bv[j] = (bias && n + j < Cout) ? __ldg(bias + n + j) : 0.f;
+  }
+}
+
+// Drain one accumulator row (this thread's TMEM lane).  All 32 lanes execute the tcgen05.ld (warp-collective) even
+// when their pixel is outside the image.  gn (optional): per-(sample, channel) sum / sum of squares of the fp32
+// results; sb = this lane's sample index.
+// pipe = true (1x1 GEMMs, whose CTAs are read-out bound): the load of chunk i+1 is in flight while chunk i is
+// converted and stored.  The 3x3 kernels keep the serial form: their read-out hides behind the MMAs of the next
+// tile, and more aggressive TMEM reads were measured to slow the MMA pipe down.
+__device__ __forceinline__ void epilogue_rows(const TcParams& p, uint32_t taddr, int n0, bool ok, long long pix,
+                                              const float* __restrict__ bias, void* __restrict__ yv,
+                                              float* __restrict__ gn, int sb, bool pipe = false) {
+  const int ncols = min(p.bn, (p.Cout - n0 + 15) / 16 * 16);      // chunks at or beyond Cout hold nothing
+  if (!pipe) {
+    for (int c = 0; c < ncols; c += 16) {
+      uint32_t r[16];
+      float bv[16];
+      tmem_ld16(taddr + (uint32_t)c, r);
+      load_bias16(bias, n0 + c, p.Cout, bv);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      process_chunk(p, r, bv, n0 + c, ok, pix, yv, gn, sb);
+    }
+    return;
+  }
+  uint32_t ra[16], rb[16];
+  float ba[16], bb[16];
+  if (ncols > 0) { tmem_ld16(taddr, ra); load_bias16(bias, n0, p.Cout, ba); }
+  for (int c = 0; c < ncols; c += 32) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (c + 16 < ncols) { tmem_ld16(taddr + (uint32_t)(c + 16), rb); load_bias16(bias, n0 + c + 16, p.Cout, bb); }
+    process_chunk(p, ra, ba, n0 + c, ok, pix, yv, gn, sb);
+    if (c + 16 < ncols) {
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (c + 32 < ncols) { tmem_ld16(taddr + (uint32_t)(c + 32), ra); load_bias16(bias, n0 + c + 32, p.Cout, ba); }
+      process_chunk(p, rb, bb, n0 + c + 16, ok, pix, yv, gn, sb);
     }
   }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const TcParams p, const float* __restrict__ bias, void* __restrict__ yv) {
+               const TcParams p, const float* __restrict__ bias, void* __restrict__ yv, float* __restrict__ gn) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024-B alignment
   const int TC_STAGES = p.nstages, TC_STAGE_BYTES = p.stage_bytes;
@@ -245,16 +377,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     long long pix;
     bool ok;
+    int sb = b;
     if (p.flat) {
       pix = m0 + row;
       ok = pix < p.P;
+      if (gn) sb = (int)(pix / p.gnN);
     } else {
       const int ty = row / p.TW, tx = row - ty * p.TW;
       const int oh = oh0 + ty, ow = ow0 + tx;
       ok = oh < p.Ho && ow < p.Wo;
       pix = ((long long)b * p.Ho + oh) * p.Wo + ow;
     }
-    epilogue_rows(p, tmem_base + ((uint32_t)(lg * 32) << 16), n0, ok, pix, bias, yv);
+    if (p.am_ncls) epilogue_argmax(p, tmem_base + ((uint32_t)(lg * 32) << 16), ok, pix, bias);
+    else epilogue_rows(p, tmem_base + ((uint32_t)(lg * 32) << 16), n0, ok, pix, bias, yv, gn, sb, p.flat != 0);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -281,7 +416,7 @@ constexpr int HL_B_MAX = 6;
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const TcParams p, const float* __restrict__ bias, void* __restrict__ yv, int total_tiles,
-                    int ntile_n) {
+                    int ntile_n, float* __restrict__ gn) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int nB = p.nstages;                       // weight ring depth
@@ -391,8 +526,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int oh = oh0 + ty, ow = ow0 + tx;
         const bool ok = oh < p.Ho && ow < p.Wo;
         const long long pix = ((long long)b * p.Ho + oh) * p.Wo + ow;
-        epilogue_rows(p, tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * 256u + sub * 128u, n0, ok, pix,
-                      bias, yv);
+        const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * 256u + sub * 128u;
+        if (p.am_ncls) epilogue_argmax(p, trow, ok, pix, bias);
+        else epilogue_rows(p, trow, n0, ok, pix, bias, yv, gn, b);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -414,7 +550,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                           const TcParams p, const float* __restrict__ bias, void* __restrict__ yv, int total_tiles,
-                          int ntile_n) {
+                          int ntile_n, float* __restrict__ gn) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int NS = p.nstages;
@@ -495,7 +631,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
       mbar_wait(bar_tfull + 8 * buf, (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       epilogue_rows(p, tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * buf_stride, n0, pix < p.P, pix, bias,
-                    yv);
+                    yv, gn, gn ? (int)(pix / p.gnN) : 0, true);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
@@ -509,12 +645,24 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
 }
 
 // ------------------------------------------------------------------ host side: tensor maps
+inline int use_pgemm_env() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CAMRADEPTH_TC_PGEMM"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v;
+}
 }  // namespace
 
-extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
-                               float* gn_sums, crd_stream_t stream) {
-  CRD_REQUIRE(d && x && w && y);
-  CRD_REQUIRE(gn_sums == nullptr);                       // fused GroupNorm statistics: not in this revision
+namespace {
+struct ArgmaxOut { int ncls; void* m0; int ld0; void* m1; int ld1; float* mf; };
+}
+
+static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
+                            float* gn_sums, const ArgmaxOut* am, crd_stream_t stream) {
+  CRD_REQUIRE(d && x && w && (y || am));
+  CRD_REQUIRE(!am || (am->ncls > 0 && am->ncls <= d->Cout && d->Cout <= 128 && !gn_sums && !d->accumulate &&
+                      d->act == CRD_ACT_NONE && !use_pgemm_env()));
+  // fused GroupNorm statistics: sums of the fp32 results (after the bias), so no activation / accumulation
+  CRD_REQUIRE(gn_sums == nullptr || (d->act == CRD_ACT_NONE && !d->accumulate));
   CRD_REQUIRE(d->in_dtype == CRD_BF16 && (d->out_dtype == CRD_BF16 || d->out_dtype == CRD_F32));
   CRD_REQUIRE(d->stride == 1 && !d->out_nchw && d->Ho == d->H && d->Wo == d->W);
   CRD_REQUIRE(d->Cin % 8 == 0 && d->ldx % 8 == 0 && d->ldy % 8 == 0);
@@ -533,6 +681,11 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
   p.woff = d->w_koff;
   p.kchunks = (d->Cin + TC_BK - 1) / TC_BK;
   p.ldy = d->ldy; p.out_f32 = d->out_dtype == CRD_F32; p.act = d->act; p.accumulate = d->accumulate;
+  p.gnN = d->H * d->W;
+  p.am_ncls = am ? am->ncls : 0;
+  p.am0 = am ? (bf16*)am->m0 : nullptr; p.am_ld0 = am ? am->ld0 : 0;
+  p.am1 = am ? (bf16*)am->m1 : nullptr; p.am_ld1 = am ? am->ld1 : 0;
+  p.amf = am ? am->mf : nullptr;
   // spatial patch: 16 wide unless the image is narrower
   p.TW = d->W >= 16 ? 16 : (d->W >= 8 ? 8 : 4);
   p.TH = TC_BM / p.TW;
@@ -589,13 +742,12 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
     const int smem = HL_A_STAGES * HL_A_BYTES + p.nstages * b_bytes + 1024 + 256;
     const int total_tiles = p.tiles_w * p.tiles_h * d->B * ntile;
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-    conv_tc_halo_kernel<<<grid, TC_THREADS, smem, s>>>(map_a, map_b, p, bias, y, total_tiles, ntile);
+    conv_tc_halo_kernel<<<grid, TC_THREADS, smem, s>>>(map_a, map_b, p, bias, y, total_tiles, ntile, gn_sums);
     CRD_LAUNCH_CHECK();
     return 0;
   }
-  static int use_pgemm = -1;
   // measured slower than two one-tile CTAs per SM (8 epilogue warps instead of 4): opt-in only
-  if (use_pgemm < 0) { const char* e = getenv("CAMRADEPTH_TC_PGEMM"); use_pgemm = (e && e[0] == '1') ? 1 : 0; }
+  const int use_pgemm = use_pgemm_env();
   if (use_pgemm && p.flat) {
     static unsigned long long attr_pg = 0;
     if (int e = ensure_smem_attr(gemm_tc_persistent_kernel, 227 * 1024, attr_pg)) return e;
@@ -614,14 +766,14 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
     if (rc) return rc;
     const int total_tiles = crd_div_up(P, TC_BM) * ntile;
     const int grid = total_tiles < pg_sms ? total_tiles : pg_sms;
-    gemm_tc_persistent_kernel<<<grid, TC_THREADS, smem, s>>>(map_a, map_b, p, bias, y, total_tiles, ntile);
+    gemm_tc_persistent_kernel<<<grid, TC_THREADS, smem, s>>>(map_a, map_b, p, bias, y, total_tiles, ntile, gn_sums);
     CRD_LAUNCH_CHECK();
     return 0;
   }
   const int gx = p.flat ? crd_div_up(P, TC_BM) : p.tiles_w * p.tiles_h * d->B;
   // N tiles of equal width <= 256 (one pass over A per tile; rows past Cout are zero-filled by TMA)
   int ntile = (d->Cout + 255) / 256;
-  {
+  if (!am) {
     // small problems (fewer CTAs than two per SM) are latency-bound by the serial accumulator read-out of one
     // wide tile: narrower N tiles (>= 32 columns) spread it over the idle SMs; A is re-read from L2, which is
     // free at these sizes
@@ -642,9 +794,20 @@ extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void
   cuuint32_t boxb[2] = {TC_BK, (cuuint32_t)p.bn};
   rc = make_map(&map_b, w, 2, dimsb, strb, boxb);
   if (rc) return rc;
-  conv_tc_kernel<<<dim3(gx, ntile), TC_THREADS, smem, s>>>(map_a, map_b, p, bias, y);
+  conv_tc_kernel<<<dim3(gx, ntile), TC_THREADS, smem, s>>>(map_a, map_b, p, bias, y, gn_sums);
   CRD_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
+                               float* gn_sums, crd_stream_t stream) {
+  return conv_fwd_tc_impl(d, x, w, bias, y, gn_sums, nullptr, stream);
+}
+extern "C" int crd_conv_argmax_tc(const crd_conv_desc* d, const void* x, const void* w, const float* bias, int ncls,
+                                  void* map0, int ld0, void* map1, int ld1, float* map_f32, crd_stream_t stream) {
+  CRD_REQUIRE(map0 || map1 || map_f32);
+  ArgmaxOut am{ncls, map0, ld0, map1, ld1, map_f32};
+  return conv_fwd_tc_impl(d, x, w, bias, nullptr, nullptr, &am, stream);
 }
 
 namespace {

@@ -87,6 +87,8 @@ class Engine:
         self._maps = {}
         self.use_tc = precision == "bf16" and os.environ.get("CAMRADEPTH_TC", "1") == "1"
         self.use_tc_wgrad = self.use_tc and os.environ.get("CAMRADEPTH_TC_WGRAD", "1") == "1"
+        # GroupNorm statistics from the accumulator read-out of the producing tcgen05 conv / GEMM
+        self.fuse_gn_stats = self.use_tc and os.environ.get("CAMRADEPTH_GN_EPILOGUE", "1") == "1"
         self._build_layers()
         self.fwd_arena = None
         self.bwd_arena = None
@@ -94,6 +96,7 @@ class Engine:
         self.timed = None
         self._grad_epoch = 0
         self._flat_own = None
+        self._grads_out = None
 
     def _timed(self, kind, name):
         if self.timed is None or (kind, name) not in self.timed:
@@ -256,21 +259,29 @@ class Engine:
         ops.im2col(x, col, L["cin_p"], L["k"], L["k"], L["stride"], L["pad"])
         return col
 
-    def conv(self, x, name, y, bias=None, act=0, accumulate=0, out_nchw=0):
+    def conv(self, x, name, y, bias=None, act=0, accumulate=0, out_nchw=0, gn=False):
+        """gn=True: the conv is followed by a GroupNorm.  On the tensor-core path the per-(sample, channel) sums are
+        produced by the accumulator read-out of the conv itself and returned (zero-initialised arena slice);
+        otherwise None is returned and the caller runs the separate statistics pass."""
         L = self.L[name]
         w = self.wpack(name, 0)
+        fuse_gn = gn and self.fuse_gn_stats and act == 0 and not accumulate
         if self._gemm_route(L, x) and not out_nchw:
             col = self._im2col(L, x, y.shape[1], y.shape[2])
             d = ops.make_desc(col, y, col.shape[-1], L["cout"], 1, 1, 1, 0, 0, act, accumulate, 0)
-            ops.conv_fwd(d, col, w, None if bias is None else self.P[bias].detach(), y, use_tc=True)
-            return
+            sums = self.fwd_arena.take(x.shape[0], L["cout"], 2) if fuse_gn else None
+            ops.conv_fwd(d, col, w, None if bias is None else self.P[bias].detach(), y, use_tc=True, gn_sums=sums)
+            return sums
         d = ops.make_desc(x, y, L["cin_p"], L["cout"], L["k"], L["k"], L["stride"], L["pad"], 0, act, accumulate,
                           out_nchw)
         b = None if bias is None else self.P[bias].detach()
         ev = self._timed("fwd", name)
-        ops.conv_fwd(d, x, w, b, y, use_tc=self.use_tc and self._tc_ok(L, x, y))
+        tc = self.use_tc and self._tc_ok(L, x, y)
+        sums = self.fwd_arena.take(x.shape[0], L["cout"], 2) if (fuse_gn and tc) else None
+        ops.conv_fwd(d, x, w, b, y, use_tc=tc, gn_sums=sums)
         if ev is not None:
             ev.record()
+        return sums
 
     def conv_dgrad(self, dy, name, dx, accumulate):
         L = self.L[name]
@@ -316,10 +327,12 @@ class Engine:
         if db is not None:
             ops.col_sum(dy, db, L["cout"])
 
-    def gn_fwd(self, x, prefix, G, want_xbar=False):
+    def gn_fwd(self, x, prefix, G, want_xbar=False, sums=None):
+        """sums: per-(b,c) sum / sum of squares already produced by the conv that wrote x (Engine.conv(gn=True))."""
         B, N, C = ops._bnc(x)
-        sums = self.fwd_arena.take(B, C, 2)
-        ops.chan_stats(x, sums)
+        if sums is None:
+            sums = self.fwd_arena.take(B, C, 2)
+            ops.chan_stats(x, sums)
         ab = self._empty(B, C, 2, dtype=torch.float32)
         mr = self._empty(B, G, 2, dtype=torch.float32)
         xbar = self._empty(B, C, dtype=torch.float32) if want_xbar else None
@@ -371,8 +384,8 @@ class Engine:
         Wo = (W + 2 * L["pad"] - L["k"]) // L["stride"] + 1
         C = cfg.dims[s]
         y = self._empty(B, Ho, Wo, C)
-        self.conv(xin, name + ".proj.weight", y, bias=name + ".proj.bias")
-        ab, mr, _ = self.gn_fwd(y, name + ".norm", C // cfg.gn_div)
+        sums = self.conv(xin, name + ".proj.weight", y, bias=name + ".proj.bias", gn=True)
+        ab, mr, _ = self.gn_fwd(y, name + ".norm", C // cfg.gn_div, sums=sums)
         x0 = self._empty(B, Ho, Wo, C, dtype=torch.float32)
         ops.affine_act(y, x0, ab, None, ops.ACT_NONE)
         rec = dict(xin=xin, y=y, ab=ab, mr=mr) if save else None
@@ -407,8 +420,8 @@ class Engine:
         if sr > 1:
             Hs, Ws = H // sr, W // sr
             xs = self._empty(B, Hs, Ws, C)
-            self.conv(x1, p + ".attn.sr.weight", xs, bias=p + ".attn.sr.bias")
-            ab_s, mr_s, _ = self.gn_fwd(xs, p + ".attn.norm", G)
+            sums_s = self.conv(x1, p + ".attn.sr.weight", xs, bias=p + ".attn.sr.bias", gn=True)
+            ab_s, mr_s, _ = self.gn_fwd(xs, p + ".attn.norm", G, sums=sums_s)
             xsn = self._empty(B, Hs, Ws, C)
             ops.affine_act(xs, xsn, ab_s, None, ops.ACT_NONE)
             kin = xsn
@@ -433,8 +446,8 @@ class Engine:
         x2 = self._empty(B, H, W, C)
         ops.affine_act(x_mid, x2, ab2, None, ops.ACT_NONE)
         h1 = self._empty(B, H, W, rC)
-        self.conv(x2, p + ".mlp1.fc1.weight", h1, bias=p + ".mlp1.fc1.bias")
-        ab_m1, mr_m1, _ = self.gn_fwd(h1, p + ".mlp1.norm1", rC // cfg.gn_div)
+        sums_m1 = self.conv(x2, p + ".mlp1.fc1.weight", h1, bias=p + ".mlp1.fc1.bias", gn=True)
+        ab_m1, mr_m1, _ = self.gn_fwd(h1, p + ".mlp1.norm1", rC // cfg.gn_div, sums=sums_m1)
         h2 = self._empty(B, H, W, rC)
         ops.dwconv_fwd(h1, ab_m1, self.P[p + ".mlp1.dwconv.dwconv.weight"].detach(),
                        self.P[p + ".mlp1.dwconv.dwconv.bias"].detach(), h2)
@@ -524,8 +537,8 @@ class Engine:
         L = self.L[name]
         B, H, W, _ = x.shape
         y = self._empty(B, H, W, L["cout"])
-        self.conv(x, name, y)
-        ab, mr, _ = self.gn_fwd(y, prefix + ".model.1", L["cout"] // self.cfg.gn_div)
+        sums = self.conv(x, name, y, gn=True)
+        ab, mr, _ = self.gn_fwd(y, prefix + ".model.1", L["cout"] // self.cfg.gn_div, sums=sums)
         ops.affine_act(y, dest, ab, post, act)
         return dict(x=x, y=y, ab=ab, mr=mr, post=post) if save else None
 
@@ -661,6 +674,25 @@ class Engine:
         self.conv(F[..., :MID], name + ".weight", lg, bias=name + ".bias")
         return lg
 
+    def seg_map(self, F, name, ncls, map0=None, map1=None, map_f32=None):
+        """Seg_Block (utils.py:95-100) for heads whose logits feed nothing but the argmax: map = argmax_c(conv) / ncls
+        written into the given channel views / fp32 map.  Tensor-core path: fused into the conv's accumulator
+        read-out (fp32 logits, never materialised); otherwise conv + argmax_map."""
+        L = self.L[name + ".weight"]
+        x = F[..., :MID]
+        if self.use_tc and self._tc_ok(L, x, None):
+            B, H, W, _ = F.shape
+            d = ops.make_desc(x, x, L["cin_p"], L["cout"], 3, 3, 1, 1, out_dtype=ops.BF16)
+            ops.conv_argmax(d, x, self.wpack(name + ".weight", 0), self.P[name + ".bias"].detach(), ncls, map0, map1,
+                            map_f32)
+            return
+        lg = self.seg_logits(F, name, torch.float32)
+        for m in (map0, map1):
+            if m is not None:
+                ops.argmax_map(lg, ncls, m, None)
+        if map_f32 is not None:
+            ops.argmax_map(lg, ncls, None, map_f32)
+
     # ------------------------------------------------------------------ whole forward
     def forward(self, x, train, masks=None, save=True):
         cfg = self.cfg
@@ -746,15 +778,10 @@ class Engine:
             FS4 = self._feat(B, 16 * h0, 16 * w0, FW)
             S["S0"] = self.dec_fwd("seg_upsample.0", F3, None, FS4[..., :MID], d2[4], save)
             if cfg.sup:
-                lg = self.seg_logits(FS4, "seg_conv_stage_4", self.tdtype)
-                ops.argmax_map(lg, cfg.num_classes, FS4[..., MID:MID + 1], None)
-                ops.argmax_map(lg, cfg.num_classes, F4[..., MID + 1:MID + 2], None)
+                self.seg_map(FS4, "seg_conv_stage_4", cfg.num_classes, FS4[..., MID:MID + 1], F4[..., MID + 1:MID + 2])
             if cfg.unsup:
-                lg = self.seg_logits(FS4, "unsup_stage_4", self.tdtype)
                 j = MID + 1 + int(cfg.sup)
-                ops.argmax_map(lg, 19, F4[..., j:j + 1], None)
-                if not cfg.sup:
-                    ops.argmax_map(lg, 19, FS4[..., MID:MID + 1], None)
+                self.seg_map(FS4, "unsup_stage_4", 19, F4[..., j:j + 1], None if cfg.sup else FS4[..., MID:MID + 1])
         inter4, S["DA4"] = self.da_fwd("depth_activation_4", F4, save)
         ops.nchw_to_nhwc(inter4, F4[..., MID:MID + 1])
 
@@ -774,10 +801,9 @@ class Engine:
                 ops.nhwc_to_nchw(lg, final_seg)
                 ops.argmax_map(lg, cfg.num_classes, F5[..., MID + 1:MID + 2], None)
             if cfg.unsup:
-                lg = self.seg_logits(FS5, "unsup_final", self.tdtype)
                 unsup_map = self._empty(B, 1, H, W, dtype=f32)
                 j = MID + 1 + int(cfg.sup)
-                ops.argmax_map(lg, 19, F5[..., j:j + 1], unsup_map)
+                self.seg_map(FS5, "unsup_final", 19, F5[..., j:j + 1], None, unsup_map)
         final_depth, S["DA5"] = self.da_fwd("depth_activation_5", F5, save)
         outs = dict(final_depth=final_depth, inter3=inter3, inter4=inter4, final_seg=final_seg, unsup_map=unsup_map)
         return outs, (S if save else None)
@@ -785,6 +811,17 @@ class Engine:
     # ------------------------------------------------------------------ whole backward
     def backward(self, S, g_final, g3, g4, g_seg, flat_grad=None, on_bucket=None):
         """-> dict name -> fp32 grad view (params without a gradient path are absent)."""
+        for tag in self.backward_steps(S, g_final, g3, g4, g_seg, flat_grad):
+            if on_bucket:
+                on_bucket(tag)
+        grads, self._grads_out = self._grads_out, None
+        return grads
+
+    def backward_steps(self, S, g_final, g3, g4, g_seg, flat_grad=None):
+        """The backward program as a generator: runs up to the next point where a bucket of the flat gradient buffer
+        is final, yields its tag ("heads", "decoder", "stage3" .. "stage0") and continues on the next `next()`.
+        Callers can start the bucket's all-reduce (parallel.py) or close one CUDA-graph capture and open the next
+        (graphs.GraphedDataParallelStep) at every yield.  The gradient dict is left in `self._grads_out`."""
         cfg = self.cfg
         B, H, W = S["B"], S["H"], S["W"]
         f32 = torch.float32
@@ -871,8 +908,7 @@ class Engine:
         ops.nhwc_to_nchw(dF3[..., MID:MID + 1], t3)
         ops.add_f32(d3, t3)
         self.da_bwd("depth_activation_3", S["DA3"], d3, dF3, True)
-        if on_bucket:
-            on_bucket("heads")
+        yield "heads"
         # ---- pyramid
         stage_T = S["stage_T"]
         dstage = [self._empty(*t.shape) for t in stage_T]
@@ -890,8 +926,7 @@ class Engine:
                            False)
         del dF1, dcat
         self.convlayer_bwd("from_encoder_1", S["fe1"], dE1, dstage[3], False)
-        if on_bucket:
-            on_bucket("decoder")
+        yield "decoder"
         # ---- encoder, last stage first
         for s in (3, 2, 1, 0):
             dx = torch.zeros(*stage_T[s].shape, dtype=f32, device=self.device)
@@ -899,13 +934,13 @@ class Engine:
             for i in reversed(range(cfg.depths[s])):
                 self.block_bwd(s, i, S["blk"][s][i], dx)
             self.pe_bwd(s, S["pe"][s], dx, dstage[s - 1] if s > 0 else None, True)
-            if on_bucket:
-                on_bucket(f"stage{s}")
-        grads = dict(self.pg)
-        for n in self.no_grad_names(sup_grad):
-            grads.pop(n, None)
-        self.pg = None
-        return grads
+            if s == 0:
+                grads = dict(self.pg)
+                for n in self.no_grad_names(sup_grad):
+                    grads.pop(n, None)
+                self.pg = None
+                self._grads_out = grads
+            yield f"stage{s}"
 
     def no_grad_names(self, sup_grad=True):
         """Parameters with no gradient path: argmax-fed heads; the whole seg branch if unsupervised."""

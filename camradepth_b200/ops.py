@@ -94,6 +94,15 @@ def conv_fwd(desc, x, w, bias, y, use_tc=False, gn_sums=None):
         K.crd_conv_fwd(ctypes.byref(desc), P(x), P(w), P(bias), P(y), stream())
 
 
+def conv_argmax(desc, x, w, bias, ncls, map0=None, map1=None, map_f32=None):
+    """tcgen05 conv whose read-out writes argmax_c / ncls into channel views map0 / map1 (B,H,W,1 slices of NHWC
+    bf16 buffers) and / or an fp32 (B,1,H,W) tensor; the logits are not stored."""
+    for m in (map0, map1):
+        assert m is None or m.dtype == torch.bfloat16
+    K.crd_conv_argmax_tc(ctypes.byref(desc), P(x), P(w), P(bias), ncls, P(map0), 0 if map0 is None else _ld(map0),
+                         P(map1), 0 if map1 is None else _ld(map1), P(map_f32), stream())
+
+
 def conv_wgrad(desc, x, dy, dw, use_tc=False, db=None):
     """db (tensor-core 1x1 path only): the bias gradient is accumulated by the same kernel."""
     if use_tc and db is not None:

@@ -36,13 +36,21 @@ def bucket_ranges(names, offsets, tag):
 
 
 class DataParallel(nn.Module):
-    def __init__(self, module, process_group=None):
+    """global_loss_mean=True (default): the camradepth_b200 losses become masked means over the valid pixels of the
+    WHOLE data-parallel batch, like the reference's single-process nn.DataParallel computes them on the gathered
+    outputs (runner.py:193-203); False keeps per-rank means (the torch DDP convention)."""
+
+    def __init__(self, module, process_group=None, global_loss_mean=True):
         super().__init__()
         self.module = module
         self.process_group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self._works = []
         self.require_backward_grad_sync = True
+        self.global_loss_mean = bool(global_loss_mean)
+        if hasattr(module, "_engines"):              # a camradepth_b200.CamRaDepth (the CPU unit tests wrap a stand-in)
+            from . import losses
+            losses.set_data_parallel(self.world if self.global_loss_mean else 1, process_group)
         if self.world > 1:
             with torch.no_grad():
                 for p in module.parameters():          # one initial broadcast (not one per step)

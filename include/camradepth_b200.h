@@ -83,6 +83,13 @@ CRD_API int crd_conv_wgrad(const crd_conv_desc* d, const void* x, const void* dy
  * [B][Cout][2]) receives per-(sample, channel) sum / sum-of-squares of the fp32 accumulators. */
 CRD_API int crd_conv_fwd_tc(const crd_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                     float* gn_sums, crd_stream_t stream);
+/* Seg_Block heads whose logits are only consumed by argmax (seg_conv_stage_4 / unsup_stage_4 / unsup_final,
+ * CamRaDepth.py:128-135,155-162 with utils.py:95-100): 3x3 conv (Cout <= 128) whose accumulator read-out takes the
+ * per-pixel argmax over the first ncls channels (first maximum wins) and writes argmax / ncls to up to two bf16
+ * NHWC channels (map0 / map1, pixel strides ld0 / ld1 in elements) and / or an fp32 (B,1,H,W) map; the logits
+ * are never materialised. */
+CRD_API int crd_conv_argmax_tc(const crd_conv_desc* d, const void* x, const void* w, const float* bias, int ncls,
+                       void* map0, int ld0, void* map1, int ld1, float* map_f32, crd_stream_t stream);
 CRD_API int crd_conv_wgrad_tc(const crd_conv_desc* d, const void* x, const void* dy, float* dw, crd_stream_t stream);
 /* 1x1 contractions with a bias (encoder q / k / fc1 / fc2 Conv1d, simplified_attention.py:16-21,66-67): the weight
  * gradient and the bias gradient db[co] += sum_pixels dY from one pass over dY (an extra MMA against ones). */

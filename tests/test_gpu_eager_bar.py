@@ -8,8 +8,9 @@ makes (conv2d, group_norm, gelu, upsample_bicubic2d, bmm, max, smooth_l1), fp32 
 bf16 autocast for the speed comparison.  The oracle is only the checker / comparison arm here; nothing in the
 product path touches it.
 
-Tolerance (bf16 product vs fp32 eager oracle at BASELINE's B=32, 192x416): final depth rel-L2 <= 1e-2, loss
-within 1e-2, global gradient rel-L2 <= 3e-2 and cosine >= 0.999.
+Tolerance (bf16 product vs fp32 eager oracle at 192x416; base at BASELINE's B=32, the segmentation variants of
+BASELINE configs 3 / 4 at B=8): final depth rel-L2 <= 1e-2 (tests/golden_util.py), loss within 1e-2, global gradient
+rel-L2 <= 3e-2 and cosine >= 0.999, supervised logits rel-L2 <= 2e-2, argmax map flip rate <= 5 %.
 """
 import json
 import os
@@ -18,7 +19,7 @@ import time
 import pytest
 import torch
 
-from tests.golden_util import relerr
+from tests.golden_util import relerr, depth_tol
 
 pytestmark = pytest.mark.gpu
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
@@ -38,15 +39,16 @@ def _oracle_step_cuda(O, cfg, sd, batch, masks, autocast):
     return pred, loss
 
 
-def test_full_size_parity_and_eager_time():
+@pytest.mark.parametrize("variant,B", [("base", 32), ("supervised_seg", 8), ("sup_unsup_seg", 8), ("unsupervised_seg", 8)])
+def test_full_size_parity_and_eager_time(variant, B):
     import camradepth_b200 as C
     from oracle import camradepth_oracle as O
     from camradepth_b200.synthetic import make_batch
-    B, H, W = 32, 192, 416
+    H, W = 192, 416
     dev = torch.device("cuda:0")
-    cfg = O.Cfg("base")
+    cfg = O.Cfg(variant)
     sd0 = O.init_state_dict(cfg, seed=5, perturb=0.02)
-    batch = {k: v.to(dev) for k, v in make_batch(B, H, W, seed=9).items()}
+    batch = {k: v.to(dev) for k, v in make_batch(B, H, W, seed=9, input_channels=cfg.cin).items()}
     masks = O.make_masks(cfg, B, seed=11)
     masks = ([t.to(dev) for t in masks[0]], [t.to(dev) for t in masks[1]])
     sd = {k: v.detach().clone().to(dev).requires_grad_(True) for k, v in sd0.items()}
@@ -55,32 +57,42 @@ def test_full_size_parity_and_eager_time():
     pred_o, loss_o = _oracle_step_cuda(O, cfg, sd, batch, masks, autocast=False)
     grads_o = {k: v.grad.detach().clone() for k, v in sd.items() if v.grad is not None}
     depth_o = pred_o["depth"]["final_depth"].detach().clone()
-    loss_o = float(loss_o)
+    seg_o = None if pred_o["seg"]["final_seg"] is None else pred_o["seg"]["final_seg"].detach().clone()
+    umap_o = None if pred_o["seg"]["unsup_map"] is None else pred_o["seg"]["unsup_map"].detach().clone()
+    loss_o = float(loss_o.detach())
     del pred_o
 
     # --- product, bf16, same weights / inputs / stochastic masks
-    C.set_model("base")
+    C.set_model(variant)
     m = C.CamRaDepth(input_channels=C.args.input_channels, precision="bf16")
     m.load_state_dict(sd0, strict=True)
     m = m.cuda().train()
     m.set_stochastic_masks(masks[0], masks[1])
-    crit = C.MaskedSmoothL1Loss()
+    crit, crit_s = C.MaskedSmoothL1Loss(), C.MaskedFocalLoss()
     pred = m(batch["image"])
     inter = pred["depth"]["intermediate_depths"]
     lf = crit(pred["depth"]["final_depth"], batch["gt_final"])
     l4 = crit(inter[-1].squeeze(1), batch["gt_s4"].squeeze(1))
     l3 = crit(inter[-2].squeeze(1), batch["gt_s3"].squeeze(1))
-    loss = (lf + l4 + l3) / 3.4
+    ls = crit_s(pred["seg"]["final_seg"], batch["gt_seg"]) if cfg.sup else 0
+    loss = (lf + l4 + l3 + 0.2 * ls) / 3.4
     loss.backward()
     torch.cuda.synchronize()
+    C.set_model("base")
     e = relerr(pred["depth"]["final_depth"], depth_o)
+    e_seg = None if seg_o is None else relerr(pred["seg"]["final_seg"], seg_o)
+    flips = None if umap_o is None else float((pred["seg"]["unsup_map"] != umap_o.float()).float().mean())
+    assert sorted(n for n, p in m.named_parameters() if p.grad is None) == sorted(n for n in sd if n not in grads_o)
     num = den = dot = n1 = n2 = 0.0
     for n, p in m.named_parameters():
+        if p.grad is None:
+            continue
         a, b = p.grad.double().flatten(), grads_o[n].double().flatten()
         num += float((a - b).pow(2).sum()); den += float(b.pow(2).sum())
         dot += float(a @ b); n1 += float(a @ a); n2 += float(b @ b)
     grel, gcos = (num / den) ** 0.5, dot / (n1 * n2) ** 0.5
-    rep = {"case": "base_32x192x416_train_vs_eager_oracle_on_gpu", "precision": "bf16", "final_depth_rel_l2": e,
+    rep = {"case": f"{variant}_{B}x192x416_train_vs_eager_oracle_on_gpu", "precision": "bf16", "final_depth_rel_l2": e,
+           "final_seg_rel_l2": e_seg, "unsup_map_flip_rate": flips,
            "loss": float(loss), "loss_oracle": loss_o, "global_grad_rel_l2": grel, "global_grad_cos": gcos}
 
     # --- how long the eager execution takes on this GPU (fwd + losses + bwd; the optimizer is left out, which
@@ -103,15 +115,18 @@ def test_full_size_parity_and_eager_time():
             torch.backends.cudnn.allow_tf32 = False
             torch.backends.cuda.matmul.allow_tf32 = False
 
-    rep["eager_fp32_ms"] = 1e3 * timed(False, False)
-    rep["eager_tf32_ms"] = 1e3 * timed(False, True)
-    rep["eager_bf16_autocast_ms"] = 1e3 * timed(True, True)
-    rep["eager_note"] = "fwd+loss+bwd only (no optimizer), B=32 192x416, median of 3 after 1 warm-up"
+    if variant == "base":
+        rep["eager_fp32_ms"] = 1e3 * timed(False, False)
+        rep["eager_tf32_ms"] = 1e3 * timed(False, True)
+        rep["eager_bf16_autocast_ms"] = 1e3 * timed(True, True)
+        rep["eager_note"] = "fwd+loss+bwd only (no optimizer), B=32 192x416, median of 3 after 1 warm-up"
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, "parity_report.jsonl"), "a") as fh:
         fh.write(json.dumps(rep) + "\n")
     print(json.dumps(rep))
-    assert e < 1e-2, e
+    assert e < depth_tol("bf16"), e
+    assert e_seg is None or e_seg < 2e-2, e_seg
+    assert flips is None or flips < 5e-2, flips
     assert abs(float(loss) - loss_o) < 1e-2 * max(1.0, abs(loss_o))
     assert grel < 3e-2, grel
     assert gcos > 0.999, gcos

@@ -101,3 +101,46 @@ def test_graphed_inference_matches_eager():
     out3 = g(b["image"])["depth"]["final_depth"]
     assert rel(out3, ref3) < 5e-3
     assert rel(ref3, ref) > 1e-3
+
+
+@pytest.mark.parametrize("variant", ["base", "supervised_seg"])
+def test_phased_step_matches_autograd_step(variant):
+    """GraphedDataParallelStep (explicit forward / loss / backward phases, no autograd; one process => ONE graph)
+    must reproduce the autograd-driven training step: same loss, same parameter updates."""
+    import camradepth_b200 as C
+    from camradepth_b200.graphs import GraphedDataParallelStep
+    from camradepth_b200.synthetic import make_batch
+    C.set_model(variant)
+    try:
+        b = {k: v.cuda() for k, v in make_batch(2, 64, 96, seed=4).items()}
+
+        def build():
+            torch.manual_seed(0)
+            m = C.CamRaDepth(precision="fp32").cuda().eval()
+            return m, C.diffGradNorm(m.parameters(), lr=1e-3)
+
+        m1, o1 = build()
+        ts = C.TrainStep(m1, o1, update_interval=1, supervised_seg=variant == "supervised_seg")
+        m2, o2 = build()
+        g = GraphedDataParallelStep(m2, o2, b, warmup=2)
+        ref = []
+        ts.start_epoch()
+        for _ in range(5):
+            loss, stepped = ts(b)
+            assert stepped
+            ref.append(float(loss))
+        got = [float(g(b)) for _ in range(3)]        # two warm-up steps ran eagerly inside the constructor
+        torch.cuda.synchronize()
+        for a, c in zip(ref[2:], got):
+            assert abs(a - c) < 1e-4 * abs(a), (ref, got)
+        p1 = torch.cat([p.detach().flatten() for p in m1.parameters()])
+        p2 = torch.cat([p.detach().flatten() for p in m2.parameters()])
+        assert rel(p2, p1) < 1e-5
+        st1, st2 = o1.state[next(iter(m1.parameters()))], o2.state[next(iter(m2.parameters()))]
+        assert st1["step"] == st2["step"] == 5
+        # parameters without a gradient path keep grad None (SURVEY F9)
+        none1 = {n for n, p in m1.named_parameters() if p.grad is None}
+        if variant == "supervised_seg":
+            assert {n for n, p in m2.named_parameters() if p.grad is None} == {"seg_conv_stage_4.weight", "seg_conv_stage_4.bias"}
+    finally:
+        C.set_model("base")

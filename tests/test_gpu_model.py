@@ -13,7 +13,7 @@ import os
 import pytest
 import torch
 
-from tests.golden_util import golden_files, load_case, relerr, samp, oracle_run
+from tests.golden_util import golden_files, load_case, relerr, samp, oracle_run, depth_tol
 
 pytestmark = pytest.mark.gpu
 FILES = golden_files()
@@ -59,7 +59,7 @@ ATTN_KEYS = (".attn.q.", ".attn.k.", ".attn.sr.", ".attn.norm.")
 def test_model_matches_reference_golden(path, precision):
     g, cfg, sd, batch, masks = load_case(path)
     m, pred, loss, parts = run_product(g["variant"], cfg, sd, batch, masks, precision, g["train"])
-    tol = 1e-4 if precision == "fp32" else 1e-2
+    tol = depth_tol(precision, os.path.basename(path))
     e_final = relerr(pred["depth"]["final_depth"], g["final_depth"])
     e3 = relerr(pred["depth"]["intermediate_depths"][2], g["inter3"])
     e4 = relerr(pred["depth"]["intermediate_depths"][3], g["inter4"])
@@ -154,7 +154,7 @@ def test_baseline_size_vs_oracle(precision):
     batch = make_batch(1, 192, 416, seed=9)
     pred_o, loss_o, parts_o, grads_o, _ = oracle_run(cfg, sd, batch, (None, None))
     m, pred, loss, parts = run_product("base", cfg, sd, batch, (None, None), precision, False)
-    tol = 1e-4 if precision == "fp32" else 1e-2
+    tol = depth_tol(precision)
     e = relerr(pred["depth"]["final_depth"], pred_o["depth"]["final_depth"])
     assert e < tol, e
     assert abs(float(loss) - float(loss_o)) < tol * max(1.0, abs(float(loss_o)))

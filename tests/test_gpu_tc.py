@@ -58,6 +58,16 @@ def test_conv_tc_fwd_and_dgrad(case):
     torch.cuda.synchronize()
     assert rel(nchw(y, Cout), yr) < 5e-3, rel(nchw(y, Cout), yr)
     assert float(ybuf[..., :8].abs().max()) == 0 and float(ybuf[..., 8 + cout_p:].abs().max()) == 0
+    # GroupNorm statistics from the accumulator read-out: per-(sample, channel) sum and sum of squares of the fp32
+    # results (bias included), accumulated on top of the buffer's contents; 1x1 tiles may straddle samples
+    sums = torch.full((B, Cout, 2), 0.25, dtype=torch.float32, device=d)
+    y_gn = torch.zeros(B, H, W, cout_p, dtype=BF, device=d)
+    ops.conv_fwd(ops.make_desc(xb, y_gn, cin_p, Cout, k, k, 1, pad), xb, wp, bias, y_gn, use_tc=True, gn_sums=sums)
+    torch.cuda.synchronize()
+    assert torch.equal(y_gn[..., :Cout], y[..., :Cout])
+    yd = yr.detach().double()
+    assert rel(sums[..., 0] - 0.25, yd.sum((2, 3))) < 2e-4, "sum"
+    assert rel(sums[..., 1] - 0.25, (yd * yd).sum((2, 3))) < 1e-4, "sum of squares"
     # same thing on the CUDA-core path: the two must agree to accumulation-order noise
     y2 = torch.zeros(B, H, W, cout_p, dtype=BF, device=d)
     desc2 = ops.make_desc(xb, y2, cin_p, Cout, k, k, 1, pad)
@@ -141,3 +151,37 @@ def test_conv_tc_large_matches_simt():
     torch.cuda.synchronize()
     ms = t0.elapsed_time(t1) / 5
     print(f"tc wgrad 296->128 @192x416 B=2: {ms:.3f} ms, {2*B*H*W*Cout*9*Cin/ms/1e9:.1f} TFLOP/s")
+
+
+@pytest.mark.parametrize("case", [(2, 32, 48, 21), (1, 16, 32, 19), (2, 12, 20, 21)])   # halo kernel x2, plain kernel
+def test_conv_argmax_fused(case):
+    """Seg_Block head fused into the conv read-out: argmax over the fp32 accumulators, logits never stored."""
+    from camradepth_b200 import ops
+    B, H, W, ncls = case
+    Cin = 128
+    d = dev()
+    torch.manual_seed(3)
+    x = torch.randn(B, Cin, H, W, device=d)
+    w = torch.randn(ncls, Cin, 3, 3, device=d) / math.sqrt(9 * Cin)
+    bias = torch.randn(ncls, device=d) * 0.1
+    lg = F.conv2d(rnd(x, BF), rnd(w, BF), bias, padding=1)
+    xb = nhwc(x, BF, Cin + 8)[..., :Cin]
+    wp = torch.zeros(ncls, 9 * Cin, dtype=BF, device=d)
+    ops.weight_pack(w, wp, None, ncls, Cin, 9, Cin, r8(ncls), 0)
+    buf0 = torch.full((B, H, W, 136), 7.0, dtype=BF, device=d)
+    buf1 = torch.full((B, H, W, 8), 7.0, dtype=BF, device=d)
+    mf = torch.full((B, 1, H, W), 7.0, device=d)
+    desc = ops.make_desc(xb, xb, Cin, ncls, 3, 3, 1, 1, out_dtype=ops.BF16)
+    ops.conv_argmax(desc, xb, wp, bias, ncls, buf0[..., 128:129], buf1[..., 3:4], mf)
+    torch.cuda.synchronize()
+    idx = torch.round(mf * ncls).long().squeeze(1)
+    ref = lg.argmax(1)
+    top2 = lg.topk(2, dim=1).values
+    gap = top2[:, 0] - top2[:, 1]
+    bad = idx != ref
+    assert float(bad.float().mean()) < 2e-3
+    assert not bool((bad & (gap > 1e-3)).any())          # disagreements only at near-ties (accumulation order)
+    want = (idx.float() / ncls).to(BF)
+    assert torch.equal(buf0[..., 128], want) and torch.equal(buf1[..., 3], want)
+    assert float((buf0[..., :128] - 7).abs().max()) == 0 and float((buf0[..., 129:] - 7).abs().max()) == 0
+    assert float((buf1[..., :3] - 7).abs().max()) == 0 and float((buf1[..., 4:] - 7).abs().max()) == 0

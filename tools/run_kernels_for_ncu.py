@@ -18,8 +18,10 @@ wd = (torch.randn(Cin, 9 * Cout, device=d) / math.sqrt(9 * Cout)).to(BF)
 y = torch.empty(B, H, W, Cout, dtype=BF, device=d)
 dx = torch.empty(B, H, W, Cin, dtype=BF, device=d)
 dw = torch.zeros(Cout, 9 * Cin, device=d)
+gsum = torch.zeros(B, Cout, 2, device=d)
 for _ in range(int(os.environ.get("CONV_ITERS", "3"))):
-    ops.conv_fwd(ops.make_desc(x, y, Cin, Cout, 3, 3, 1, 1), x, w, None, y, use_tc=True)
+    # forward as the training step runs it: GroupNorm statistics from the accumulator read-out
+    ops.conv_fwd(ops.make_desc(x, y, Cin, Cout, 3, 3, 1, 1), x, w, None, y, use_tc=True, gn_sums=gsum)
     ops.conv_fwd(ops.make_desc(y, dx, Cout, Cin, 3, 3, 1, 1, transposed=1), y, wd, None, dx, use_tc=True)
     ops.conv_wgrad(ops.make_desc(x, y, Cin, Cout, 3, 3, 1, 1), x, y, dw, use_tc=True)
 # stage-2 Mix-FFN pieces (TMA-staged streaming kernels) and the attention score
