@@ -42,6 +42,7 @@ struct TcParams {
   int nstages, stage_bytes; // smem ring geometry: stage = A (16 KB) + B (bn * 128 B)
   int tmem_cols;            // 128 or 256
   int ldy, out_f32, act, accumulate;
+  int pipe;                 // 1x1 GEMMs: software-pipelined accumulator read-out (CAMRADEPTH_TC_PIPE, default on)
   int gnN;                  // pixels per sample (flat mode: sample of a pixel = pix / gnN) for the GroupNorm sums
   // fused conv + argmax (Seg_Block, utils.py:95-100): am_ncls > 0 -> nothing is written to y; the per-pixel
   // argmax over the first am_ncls output channels, divided by am_ncls, goes to up to two bf16 NHWC channels
@@ -96,13 +97,40 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 // warp total of value l, i.e. lanes 0..15 the channel sums and lanes 16..31 the channel sums of squares, which go
 // to gn[b][channel][2] with one fp32 atomic per lane.  `sb` is the lane's sample (flat 1x1 tiles may straddle two
 // samples: one pass per sample present in the warp), `valid` masks pixels outside the tensor.
+__device__ __forceinline__ float gn_butterfly(float (&a)[32]) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2, u1 = lane & 1;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const float send = u16 ? a[i] : a[i + 16], keep = u16 ? a[i + 16] : a[i];
+    a[i] = keep + __shfl_xor_sync(full, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float send = u8 ? a[i] : a[i + 8], keep = u8 ? a[i + 8] : a[i];
+    a[i] = keep + __shfl_xor_sync(full, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float send = u4 ? a[i] : a[i + 4], keep = u4 ? a[i + 4] : a[i];
+    a[i] = keep + __shfl_xor_sync(full, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const float send = u2 ? a[i] : a[i + 2], keep = u2 ? a[i + 2] : a[i];
+    a[i] = keep + __shfl_xor_sync(full, send, 2);
+  }
+  const float send = u1 ? a[0] : a[1], keep = u1 ? a[1] : a[0];
+  return keep + __shfl_xor_sync(full, send, 1);       // lane l: warp total of value l
+}
+
 __device__ __forceinline__ void gn_accumulate16(const float (&v)[16], bool valid, int sb, int n, int Cout,
                                                 float* __restrict__ gn) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int bmin = __reduce_min_sync(full, valid ? sb : 0x7fffffff);
   const int bmax = __reduce_max_sync(full, valid ? sb : -1);
-  const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2, u1 = lane & 1;
   for (int b = bmin; b <= bmax; b++) {
     const bool mine = valid && sb == b;
     float a[32];
@@ -112,32 +140,9 @@ __device__ __forceinline__ void gn_accumulate16(const float (&v)[16], bool valid
       a[j] = x;
       a[16 + j] = x * x;
     }
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-      const float send = u16 ? a[i] : a[i + 16], keep = u16 ? a[i + 16] : a[i];
-      a[i] = keep + __shfl_xor_sync(full, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const float send = u8 ? a[i] : a[i + 8], keep = u8 ? a[i + 8] : a[i];
-      a[i] = keep + __shfl_xor_sync(full, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const float send = u4 ? a[i] : a[i + 4], keep = u4 ? a[i + 4] : a[i];
-      a[i] = keep + __shfl_xor_sync(full, send, 4);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-      const float send = u2 ? a[i] : a[i + 2], keep = u2 ? a[i + 2] : a[i];
-      a[i] = keep + __shfl_xor_sync(full, send, 2);
-    }
-    {
-      const float send = u1 ? a[0] : a[1], keep = u1 ? a[1] : a[0];
-      a[0] = keep + __shfl_xor_sync(full, send, 1);
-    }
+    const float tot = gn_butterfly(a);
     const int ch = n + (lane & 15);
-    if (ch < Cout) atomicAdd(gn + ((long long)b * Cout + ch) * 2 + (lane >> 4), a[0]);
+    if (ch < Cout) atomicAdd(gn + ((long long)b * Cout + ch) * 2 + (lane >> 4), tot);
   }
 }
 
@@ -169,6 +174,9 @@ __device__ __forceinline__ void epilogue_argmax(const TcParams& p, uint32_t tadd
 
 // One 16-column chunk of an accumulator row: bias / GroupNorm sums / sigmoid / accumulate in registers, then one
 // 32-byte (bf16) store per thread.  `bv` holds the chunk's 16 bias values (zeros without a bias).
+__device__ __forceinline__ void store_chunk(const TcParams& p, float (&v)[16], int n, bool ok, long long pix,
+                                            void* __restrict__ yv);
+
 __device__ __forceinline__ void process_chunk(const TcParams& p, const uint32_t (&r)[16], const float (&bv)[16], int n,
                                               bool ok, long long pix, void* __restrict__ yv, float* __restrict__ gn,
                                               int sb) {
@@ -176,6 +184,11 @@ __device__ __forceinline__ void process_chunk(const TcParams& p, const uint32_t 
 #pragma unroll
   for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]) + bv[j];
   if (gn) gn_accumulate16(v, ok, sb, n, p.Cout, gn);      // warp-uniform branch, all lanes take part
+  store_chunk(p, v, n, ok, pix, yv);
+}
+
+__device__ __forceinline__ void store_chunk(const TcParams& p, float (&v)[16], int n, bool ok, long long pix,
+                                            void* __restrict__ yv) {
   if (!ok) return;
   if (p.act == CRD_ACT_SIGMOID) {
 #pragma unroll
@@ -235,7 +248,12 @@ __device__ __forceinline__ void process_chunk(const TcParams& p, const uint32_t 
 // The chunk's bias values: four 16-byte loads issued BEFORE the accumulator load is waited for (a scalar load per
 // channel behind the wait cost 40 % of the 1x1 GEMMs with wide outputs).
 __device__ __forceinline__ void load_bias16(const float* __restrict__ bias, int n, int Cout, float (&bv)[16]) {
-  if (bias && n + 16 <= Cout && ((reinterpret_cast<uintptr_t>(bias + n) & 15) == 0)) {
+  if (!bias) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) bv[j] = 0.f;
+    return;
+  }
+  if (n + 16 <= Cout && ((reinterpret_cast<uintptr_t>(bias + n) & 15) == 0)) {
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const float4 t = __ldg(reinterpret_cast<const float4*>(bias + n) + q);
@@ -243,7 +261,7 @@ __device__ __forceinline__ void load_bias16(const float* __restrict__ bias, int 
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 16; j++) bv[j] = (bias && n + j < Cout) ? __ldg(bias + n + j) : 0.f;
+    for (int j = 0; j < 16; j++) bv[j] = (n + j < Cout) ? __ldg(bias + n + j) : 0.f;
   }
 }
 
@@ -389,7 +407,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       pix = ((long long)b * p.Ho + oh) * p.Wo + ow;
     }
     if (p.am_ncls) epilogue_argmax(p, tmem_base + ((uint32_t)(lg * 32) << 16), ok, pix, bias);
-    else epilogue_rows(p, tmem_base + ((uint32_t)(lg * 32) << 16), n0, ok, pix, bias, yv, gn, sb, p.flat != 0);
+    else epilogue_rows(p, tmem_base + ((uint32_t)(lg * 32) << 16), n0, ok, pix, bias, yv, gn, sb, p.pipe != 0);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -427,6 +445,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const uint32_t bar_fullB = bars + 16 * HL_A_STAGES, bar_emptyB = bar_fullB + 8 * HL_B_MAX;
   const uint32_t bar_tfull = bar_emptyB + 8 * HL_B_MAX, bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
+  const uint32_t stats_base = bars + 256;         // [bn][2] fp32 GroupNorm accumulators (1 KiB)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nA = p.kchunks * 3;                   // (chunk, kw) activation stages per tile
@@ -510,6 +529,17 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else {
     const int lg = warp & 3;
     const int row = lg * 32 + lane;
+    // GroupNorm sums: per-CTA accumulators [bn][2] in shared memory (shared-memory atomics), flushed to the global
+    // [B][Cout][2] buffer when the CTA's tile sequence moves on to the next sample: ~256 global atomics per
+    // (CTA, sample) instead of 64 per (warp, 16-column chunk) -- the latter put 29 G atomics/s on a few hundred
+    // addresses at the dominant shape and showed up as +7 % kernel time.  Host side guarantees ntile_n == 1 here.
+    float* sacc = reinterpret_cast<float*>(smem_raw + (stats_base - smem_u32(smem_raw)));
+    const int et = threadIdx.x - 64;                      // 0..127 over the four read-out warps
+    int cur_b = -1;
+    if (gn) {
+      for (int i = et; i < 2 * p.bn; i += 128) sacc[i] = 0.f;
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+    }
     int tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
       int t = tile;
@@ -518,21 +548,68 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int th = t % p.tiles_h; t /= p.tiles_h;
       const int b = t, oh0 = th * 16, ow0 = tw * 16;
       const int buf = tcount & 1;
+      if (gn && b != cur_b) {
+        if (cur_b >= 0) {
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          for (int i = et; i < 2 * p.bn; i += 128) {
+            if ((i >> 1) < p.Cout) atomicAdd(gn + ((long long)cur_b * p.Cout + (i >> 1)) * 2 + (i & 1), sacc[i]);
+            sacc[i] = 0.f;
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+        cur_b = b;
+      }
       mbar_wait(bar_tfull + 8 * buf, (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-      for (int sub = 0; sub < 2; sub++) {
-        const int ty = (row >> 4) + 8 * sub, tx = row & 15;
-        const int oh = oh0 + ty, ow = ow0 + tx;
-        const bool ok = oh < p.Ho && ow < p.Wo;
-        const long long pix = ((long long)b * p.Ho + oh) * p.Wo + ow;
-        const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * 256u + sub * 128u;
-        if (p.am_ncls) epilogue_argmax(p, trow, ok, pix, bias);
-        else epilogue_rows(p, trow, n0, ok, pix, bias, yv, gn, b);
+      const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * 256u;
+      const int tx = row & 15, ow = ow0 + tx;
+      const int oh_a = oh0 + (row >> 4), oh_b = oh_a + 8;              // the thread's pixel in the two row halves
+      const bool ok_a = oh_a < p.Ho && ow < p.Wo, ok_b = oh_b < p.Ho && ow < p.Wo;
+      const long long pix_a = ((long long)b * p.Ho + oh_a) * p.Wo + ow, pix_b = pix_a + 8LL * p.Wo;
+      if (p.am_ncls) {
+        epilogue_argmax(p, trow, ok_a, pix_a, bias);
+        epilogue_argmax(p, trow + 128u, ok_b, pix_b, bias);
+      } else if (!gn) {
+        epilogue_rows(p, trow, n0, ok_a, pix_a, bias, yv, nullptr, b);
+        epilogue_rows(p, trow + 128u, n0, ok_b, pix_b, bias, yv, nullptr, b);
+      } else {
+        // both row halves of a 16-column chunk, then ONE butterfly over their combined sums / squares
+        const int ncols = min(p.bn, (p.Cout - n0 + 15) / 16 * 16);
+        for (int c = 0; c < ncols; c += 16) {
+          uint32_t r[16];
+          float bv[16], v[16], a[32];
+          tmem_ld16(trow + (uint32_t)c, r);
+          load_bias16(bias, n0 + c, p.Cout, bv);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            v[j] = __uint_as_float(r[j]) + bv[j];
+            const float x = ok_a ? v[j] : 0.f;
+            a[j] = x; a[16 + j] = x * x;
+          }
+          tmem_ld16(trow + 128u + (uint32_t)c, r);
+          store_chunk(p, v, n0 + c, ok_a, pix_a, yv);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            v[j] = __uint_as_float(r[j]) + bv[j];
+            const float x = ok_b ? v[j] : 0.f;
+            a[j] += x; a[16 + j] = fmaf(x, x, a[16 + j]);
+          }
+          store_chunk(p, v, n0 + c, ok_b, pix_b, yv);
+          const float tot = gn_butterfly(a);
+          const int ch = n0 + c + (lane & 15);
+          if (ch < p.Cout) atomicAdd(sacc + 2 * (c + (lane & 15)) + (lane >> 4), tot);
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);          // 4 epilogue warps -> buffer free
+    }
+    if (gn && cur_b >= 0) {
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      for (int i = et; i < 2 * p.bn; i += 128)
+        if ((i >> 1) < p.Cout) atomicAdd(gn + ((long long)cur_b * p.Cout + (i >> 1)) * 2 + (i & 1), sacc[i]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -631,7 +708,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
       mbar_wait(bar_tfull + 8 * buf, (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       epilogue_rows(p, tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * buf_stride, n0, pix < p.P, pix, bias,
-                    yv, gn, gn ? (int)(pix / p.gnN) : 0, true);
+                    yv, gn, gn ? (int)(pix / p.gnN) : 0, p.pipe != 0);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
@@ -682,6 +759,11 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
   p.kchunks = (d->Cin + TC_BK - 1) / TC_BK;
   p.ldy = d->ldy; p.out_f32 = d->out_dtype == CRD_F32; p.act = d->act; p.accumulate = d->accumulate;
   p.gnN = d->H * d->W;
+  {
+    static int pipe_env = -1;
+    if (pipe_env < 0) { const char* e = getenv("CAMRADEPTH_TC_PIPE"); pipe_env = (e && e[0] == '0') ? 0 : 1; }
+    p.pipe = (pipe_env && p.flat) ? 1 : 0;
+  }
   p.am_ncls = am ? am->ncls : 0;
   p.am0 = am ? (bf16*)am->m0 : nullptr; p.am_ld0 = am ? am->ld0 : 0;
   p.am1 = am ? (bf16*)am->m1 : nullptr; p.am_ld1 = am ? am->ld1 : 0;
@@ -739,7 +821,7 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
     cuuint32_t boxb[2] = {TC_BK, (cuuint32_t)p.bn};
     rc = make_map(&map_b, w, 2, dimsb, strb, boxb);
     if (rc) return rc;
-    const int smem = HL_A_STAGES * HL_A_BYTES + p.nstages * b_bytes + 1024 + 256;
+    const int smem = HL_A_STAGES * HL_A_BYTES + p.nstages * b_bytes + 1024 + 256 + 1024;
     const int total_tiles = p.tiles_w * p.tiles_h * d->B * ntile;
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
     conv_tc_halo_kernel<<<grid, TC_THREADS, smem, s>>>(map_a, map_b, p, bias, y, total_tiles, ntile, gn_sums);

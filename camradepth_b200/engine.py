@@ -15,6 +15,7 @@ Data layout in HBM (bf16 mode; fp32 mode stores everything as fp32):
 """
 from __future__ import annotations
 
+import contextlib
 import math
 import os
 
@@ -97,6 +98,15 @@ class Engine:
         self._grad_epoch = 0
         self._flat_own = None
         self._grads_out = None
+        # Gradient leaves (weight / bias gradients: nothing later in the backward program reads them) of the listed
+        # encoder stages run on a second stream, concurrently with the data-gradient chain.  The kernels of stages
+        # 3 / 4 occupy a fraction of the GPU each (20 .. 312 CTAs), so two streams fill SMs that one leaves idle.
+        # Joined at the end of every block (before its temporaries are released).  "" disables.
+        ls = os.environ.get("CAMRADEPTH_LEAF_STAGES", "2,3")
+        self.leaf_stages = tuple(int(t) for t in ls.split(",") if t.strip() != "")
+        self.leaf_stream = None
+        self._leaf_on = False
+        self._leaf_dirty = False
 
     def _timed(self, kind, name):
         if self.timed is None or (kind, name) not in self.timed:
@@ -301,7 +311,29 @@ class Engine:
         if ev is not None:
             ev.record()
 
+    def _leaf(self):
+        """Context for launching a gradient leaf: the side stream, ordered after everything launched so far."""
+        if not self._leaf_on or self.leaf_stream is None:
+            return contextlib.nullcontext()
+        ev = torch.cuda.Event()
+        ev.record()
+        self.leaf_stream.wait_event(ev)
+        self._leaf_dirty = True
+        return torch.cuda.stream(self.leaf_stream)
+
+    def _leaf_join(self):
+        """The main stream waits for the leaves launched since the last join."""
+        if self._leaf_dirty:
+            ev = torch.cuda.Event()
+            ev.record(self.leaf_stream)
+            torch.cuda.current_stream().wait_event(ev)
+            self._leaf_dirty = False
+
     def conv_wgrad(self, x, dy, name, bias=None):
+        with self._leaf():
+            self._conv_wgrad(x, dy, name, bias)
+
+    def _conv_wgrad(self, x, dy, name, bias=None):
         L = self.L[name]
         direct = L["taps"] == 1 and L["cmap"] is None and L["cin_p"] == L["cin"]
         g = self.pg[name]
@@ -401,6 +433,7 @@ class Engine:
         self.conv_wgrad(rec["xin"], dy, name + ".proj.weight", bias=name + ".proj.bias")
         if dxin is not None:
             self.conv_dgrad(dy, name + ".proj.weight", dxin, accumulate)
+        self._leaf_join()
 
     def block_fwd(self, s, i, x, dp, dp_mlp, save):
         cfg = self.cfg
@@ -494,7 +527,7 @@ class Engine:
                     None, None, dh1, False)
         del dh1n
         self.conv_wgrad(rec["x2"], dh1, p + ".mlp1.fc1.weight", bias=p + ".mlp1.fc1.bias")
-        dx2 = dy2   # reuse
+        dx2 = self._empty(B, H, W, C)       # not dy2: the fc2 weight gradient may still be reading it (leaf stream)
         self.conv_dgrad(dh1, p + ".mlp1.fc1.weight", dx2, False)
         self.gn_bwd(dx2, rec["x_mid"], rec["ab2"], rec["mr2"], p + ".norm2", G, ops.ACT_NONE, None, None, dx, True)
         # ---- attention branch (dx is now the grad wrt x_mid)
@@ -520,7 +553,7 @@ class Engine:
             self.conv_wgrad(rec["xsn"], dk, p + ".attn.k.weight", bias=p + ".attn.k.bias")
             dxsn = self._empty(*kshape)
             self.conv_dgrad(dk, p + ".attn.k.weight", dxsn, False)
-            dxs = dk   # reuse
+            dxs = self._empty(*kshape)      # not dk: the k weight gradient may still be reading it (leaf stream)
             self.gn_bwd(dxsn, rec["xs"], rec["ab_s"], rec["mr_s"], p + ".attn.norm", G, ops.ACT_NONE, None, None,
                         dxs, False)
             self.conv_wgrad(rec["x1"], dxs, p + ".attn.sr.weight", bias=p + ".attn.sr.bias")
@@ -529,6 +562,7 @@ class Engine:
             self.conv_wgrad(rec["x1"], dk, p + ".attn.k.weight", bias=p + ".attn.k.bias")
             self.conv_dgrad(dk, p + ".attn.k.weight", dx1, True)
         self.gn_bwd(dx1, rec["x"], rec["ab1"], rec["mr1"], p + ".norm1", G, ops.ACT_NONE, None, dxbar, dx, True)
+        self._leaf_join()
 
     # ------------------------------------------------------------------ decoder pieces
     def convlayer_fwd(self, x, prefix, dest, post, save, act=ops.ACT_GELU):
@@ -702,6 +736,7 @@ class Engine:
             self.device = x.device
             self.fwd_arena = ZeroArena(self.device)
             self.bwd_arena = ZeroArena(self.device)
+            self.leaf_stream = torch.cuda.Stream(self.device) if self.leaf_stages else None
         B, cin, H, W = x.shape
         if cin != cfg.cin:
             raise RuntimeError(f"expected {cfg.cin} input channels, got {cin}")
@@ -929,11 +964,13 @@ class Engine:
         yield "decoder"
         # ---- encoder, last stage first
         for s in (3, 2, 1, 0):
+            self._leaf_on = s in self.leaf_stages
             dx = torch.zeros(*stage_T[s].shape, dtype=f32, device=self.device)
             ops.add_f32(dx, dstage[s])
             for i in reversed(range(cfg.depths[s])):
                 self.block_bwd(s, i, S["blk"][s][i], dx)
             self.pe_bwd(s, S["pe"][s], dx, dstage[s - 1] if s > 0 else None, True)
+            self._leaf_on = False
             if s == 0:
                 grads = dict(self.pg)
                 for n in self.no_grad_names(sup_grad):

@@ -18,10 +18,15 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # 2x2..32x32-pixel feature maps of a random-init net whose class logits are near-tied, so a bf16 rounding upstream
 # flips a few map pixels by >= 1/21 and the final depth moves by ~1e-2 on its own (the reference itself shows the
 # effect: SURVEY.md §8c, max-norm 1.25e-2 under its own bf16 autocast).  That case gets 1.5e-2 and the flip rate of
-# the map is asserted separately (< 5 %).
+# the map is asserted separately (< 5 %).  The same holds at full size for every variant with a segmentation branch
+# ("seg_fullsize", tests/test_gpu_eager_bar.py, B=8 at 192x416): measured 1.7 % of the argmax-map pixels differ
+# between the bf16 path and the fp32 eager oracle (class logits agree to 1.5-1.7e-2 rel-L2), and the depth heads
+# convolve those maps (CamRaDepth.py:144,165), which moves the final depth by 0.6-1.9e-2 depending on the random
+# weights of the map channels; the base model (no maps) sits at 5e-3.  The correctness proof for these variants is
+# the fp32 mode (no flips): 1e-4 against the reference goldens for every variant.
 FP32_TOL = 1e-4
 BF16_TOL = 1e-2
-BF16_TOL_BY_CASE = {"ref_sup_unsup_seg_2x64x64_train.pt": 1.5e-2}
+BF16_TOL_BY_CASE = {"ref_sup_unsup_seg_2x64x64_train.pt": 1.5e-2, "seg_fullsize": 2.5e-2}
 
 
 def depth_tol(precision, case=None):

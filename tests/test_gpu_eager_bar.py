@@ -9,7 +9,8 @@ bf16 autocast for the speed comparison.  The oracle is only the checker / compar
 product path touches it.
 
 Tolerance (bf16 product vs fp32 eager oracle at 192x416; base at BASELINE's B=32, the segmentation variants of
-BASELINE configs 3 / 4 at B=8): final depth rel-L2 <= 1e-2 (tests/golden_util.py), loss within 1e-2, global gradient
+BASELINE configs 3 / 4 at B=8): final depth rel-L2 <= 1e-2 (base) / 2.5e-2 (variants whose depth heads read argmax
+segmentation maps, reasoning in tests/golden_util.py), loss within 1e-2, global gradient
 rel-L2 <= 3e-2 and cosine >= 0.999, supervised logits rel-L2 <= 2e-2, argmax map flip rate <= 5 %.
 """
 import json
@@ -124,7 +125,7 @@ def test_full_size_parity_and_eager_time(variant, B):
     with open(os.path.join(OUT, "parity_report.jsonl"), "a") as fh:
         fh.write(json.dumps(rep) + "\n")
     print(json.dumps(rep))
-    assert e < depth_tol("bf16"), e
+    assert e < depth_tol("bf16", "seg_fullsize" if (cfg.sup or cfg.unsup) else None), e
     assert e_seg is None or e_seg < 2e-2, e_seg
     assert flips is None or flips < 5e-2, flips
     assert abs(float(loss) - loss_o) < 1e-2 * max(1.0, abs(loss_o))

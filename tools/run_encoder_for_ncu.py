@@ -17,12 +17,19 @@ STAGES = [(48, 104, 64, 512), (24, 52, 128, 1024), (12, 26, 160, 640), (6, 13, 2
 
 
 def timed(fn, n=20):
+    """us per launch; the launches are replayed from a CUDA graph so the host (ctypes + descriptor setup, ~10 us per
+    call) does not bound the small shapes."""
     fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            fn()
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n):
-        fn()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
