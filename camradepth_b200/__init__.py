@@ -4,7 +4,7 @@ from .model import CamRaDepth, load_checkpoint_with_shape_match           # noqa
 from .losses import MaskedSmoothL1Loss, MaskedFocalLoss, MaskedMSELoss    # noqa: F401
 from .optim import diffGradNorm                                           # noqa: F401
 from .metrics import depth_metrics, mean_iou                              # noqa: F401
-from .train import TrainStep, save_checkpoint                             # noqa: F401
+from .train import TrainStep, evaluate, save_checkpoint                             # noqa: F401
 
 __all__ = ["args", "set_model", "CamRaDepth", "load_checkpoint_with_shape_match", "MaskedSmoothL1Loss",
            "MaskedFocalLoss", "MaskedMSELoss", "diffGradNorm"]

@@ -546,6 +546,28 @@ extern "C" int crd_sigmoid_bwd(const void* dy, const void* y, void* dx, int dtyp
   CRD_LAUNCH_CHECK();
   return 0;
 }
+namespace {
+// one thread per pixel, C (small, any count / alignment) consecutive channels
+template <typename T>
+__global__ void copy_channels_kernel(const T* __restrict__ src, int ld_src, T* __restrict__ dst, int ld_dst, int C,
+                                     long long npix) {
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const T* s = src + pix * ld_src;
+    T* d = dst + pix * ld_dst;
+    for (int c = 0; c < C; c++) d[c] = s[c];
+  }
+}
+}  // namespace
+extern "C" int crd_copy_channels(const void* src, int ld_src, void* dst, int ld_dst, int dtype, int C, long long npix,
+                                 crd_stream_t stream) {
+  CRD_REQUIRE(src && dst && C >= 0);
+  if (npix == 0 || C == 0) return 0;
+  CRD_DISPATCH_1(dtype, T, copy_channels_kernel<T><<<ew_blocks(npix), 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)src, ld_src, (T*)dst, ld_dst, C, npix));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
 extern "C" int crd_argmax_map(const void* logits, int dtype, int ld, int ncls, void* dst, int dst_dtype,
                               int ld_dst, float* dst_f32, long long npix, crd_stream_t stream) {
   if (npix == 0) return 0;

@@ -354,7 +354,7 @@ __global__ void attn_pv_bwd_w_kernel(const float* __restrict__ dpv, const float*
   float acc = 0.f;
 #pragma unroll 8
   for (int b = 0; b < B; b++) acc = fmaf(dpv[(long long)b * C + o], xbar[(long long)b * C + c], acc);
-  dWp[i] += acc;
+  atomicAdd(dWp + i, acc);      // batch chunks of one block may run concurrently (engine: split stages)
 }
 // block (32 channels, 8 slices of the output-channel sum) per (channel tile, sample)
 __global__ void __launch_bounds__(256) attn_pv_bwd_x_kernel(const float* __restrict__ dpv, const float* __restrict__ Wp,
@@ -440,7 +440,7 @@ __global__ void attn_out_bwd_fin_kernel(const float* __restrict__ tmp, const flo
     dpv[(long long)b * C + c] = sc * tmp[((long long)b * C + c) * 2];
     acc += sc * tmp[((long long)b * C + c) * 2 + 1];
   }
-  dbp[c] += acc;
+  atomicAdd(dbp + c, acc);
 }
 
 template <typename T>

@@ -270,6 +270,86 @@ __global__ void image_normalize_kernel(const unsigned char* __restrict__ img, fl
   }
 }
 
+// nearest-neighbour resize of a label map with the index rule of skimage.transform.resize(order=0,
+// anti_aliasing=False) = scipy.ndimage.zoom(order=0, grid_mode=True): src = floor((dst + 0.5) * in / out), clamped
+// (dataloader.py:262-268: the 416x800 and 208x400 segmentation ground truths)
+template <typename TS>
+__global__ void seg_resize_kernel(const TS* __restrict__ src, long long* __restrict__ dst, int B, int Hi, int Wi, int Ho,
+                                  int Wo) {
+  const long long total = (long long)B * Ho * Wo;
+  const double sh = (double)Hi / (double)Ho, sw = (double)Wi / (double)Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ow = (int)(i % Wo), oh = (int)((i / Wo) % Ho);
+    const long long b = i / ((long long)Wo * Ho);
+    int ih = (int)floor(((double)oh + 0.5) * sh), iw = (int)floor(((double)ow + 0.5) * sw);
+    ih = ih < Hi ? ih : Hi - 1; iw = iw < Wi ? iw : Wi - 1;
+    dst[i] = (long long)src[(b * Hi + ih) * Wi + iw];
+  }
+}
+
+// Network input straight in the engine's layout: NHWC bf16 with `ld` channels per pixel = [normalised RGB | extra
+// float planes (radar depth / u / v / velocity, already scaled by the caller like dataloader.py:301-323) | zeros]
+__global__ void pack_input_nhwc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ extra,
+                                       bf16* __restrict__ dst, int B, int H, int W, int Ce, int ld, float m0, float m1,
+                                       float m2, float s0, float s1, float s2) {
+  const long long hw = (long long)H * W, total = (long long)B * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / hw, r = i - b * hw;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = 0.f;
+    const unsigned char* p = img + i * 3;
+    v[0] = ((float)p[0] * (1.f / 255.f) - m0) / s0;
+    v[1] = ((float)p[1] * (1.f / 255.f) - m1) / s1;
+    v[2] = ((float)p[2] * (1.f / 255.f) - m2) / s2;
+    for (int c = 0; c < Ce && c < 5; c++) v[3 + c] = extra[(b * Ce + c) * hw + r];
+    store8(dst + i * ld, v);
+    for (int c = 8; c < ld; c += 8) {
+      float z[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) z[j] = 0.f;
+      store8(dst + i * ld + c, z);
+    }
+  }
+}
+
+// ---- stochastic masks (timm DropPath per call, nn.Dropout2d per (sample, channel) plane) from ONE launch ----------
+// Philox4x32-10 keyed by (seed, step counter); the counter lives in device memory and is advanced by the kernel
+// itself, so a CUDA-graph replay draws fresh masks.
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+// out[i] = u_i < keep[row(i)] ? 1 / keep : 0 ; rows [0, n_dp) have B entries (keep_dp[row]), the following n_d2 rows
+// have B*C2 entries (keep = keep_d2).  Single block: thread 0 advances the counter after everyone has read it.
+__global__ void make_masks_kernel(float* __restrict__ out, const float* __restrict__ keep_dp, int n_dp, int B, int n_d2,
+                                  int C2, float keep_d2, unsigned long long* __restrict__ state) {
+  const unsigned long long seed = state[0], step = state[1];
+  const long long n_a = (long long)n_dp * B, total = n_a + (long long)n_d2 * B * C2;
+  for (long long q = threadIdx.x; q * 4 < total; q += blockDim.x) {
+    uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const long long i = q * 4 + j;
+      if (i >= total) break;
+      const float u = (float)(c[j] >> 8) * (1.0f / 16777216.0f);          // [0, 1)
+      const float keep = i < n_a ? keep_dp[i / B] : keep_d2;
+      out[i] = u < keep ? 1.0f / keep : 0.f;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) state[1] = step + 1;
+}
+
 inline int red_blocks(long long n) {
   long long b = (n + 1023) / 1024;
   return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
@@ -361,6 +441,37 @@ extern "C" int crd_minpool3x3s2(const float* x, float* y, int B, int H, int W, c
   const long long total = (long long)B * Ho * Wo;
   if (total == 0) return 0;
   minpool_kernel<<<red_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, Ho, Wo);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_seg_resize_nearest(const void* src, int src_is_u8, long long* dst, int B, int Hi, int Wi, int Ho,
+                                      int Wo, crd_stream_t stream) {
+  const long long total = (long long)B * Ho * Wo;
+  if (total == 0) return 0;
+  CRD_REQUIRE(Hi > 0 && Wi > 0);
+  if (src_is_u8) seg_resize_kernel<unsigned char><<<red_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+        (const unsigned char*)src, dst, B, Hi, Wi, Ho, Wo);
+  else seg_resize_kernel<long long><<<red_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+        (const long long*)src, dst, B, Hi, Wi, Ho, Wo);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_pack_input_nhwc(const unsigned char* img, const float* extra, void* dst, int B, int H, int W, int Ce,
+                                   int ld, const float* mean3_host, const float* std3_host, crd_stream_t stream) {
+  const long long total = (long long)B * H * W;
+  if (total == 0) return 0;
+  CRD_REQUIRE(img && dst && ld >= 8 && ld % 8 == 0 && Ce >= 0 && Ce <= 5 && (Ce == 0 || extra));
+  pack_input_nhwc_kernel<<<red_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+      img, extra, (bf16*)dst, B, H, W, Ce, ld, mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0], std3_host[1],
+      std3_host[2]);
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int crd_make_masks(float* out, const float* keep_dp, int n_dp, int B, int n_d2, int C2, float keep_d2,
+                              unsigned long long* state, crd_stream_t stream) {
+  CRD_REQUIRE(out && state && (n_dp == 0 || keep_dp) && keep_d2 > 0.f);
+  if ((long long)n_dp * B + (long long)n_d2 * B * C2 == 0) return 0;
+  make_masks_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(out, keep_dp, n_dp, B, n_d2, C2, keep_d2, state);
   CRD_LAUNCH_CHECK();
   return 0;
 }

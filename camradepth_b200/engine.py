@@ -98,6 +98,7 @@ class Engine:
         self._grad_epoch = 0
         self._flat_own = None
         self._grads_out = None
+        self._mask_state = None
         # Gradient leaves (weight / bias gradients: nothing later in the backward program reads them) of the listed
         # encoder stages run on a second stream, concurrently with the data-gradient chain.  The kernels of stages
         # 3 / 4 occupy a fraction of the GPU each (20 .. 312 CTAs), so two streams fill SMs that one leaves idle.
@@ -107,6 +108,17 @@ class Engine:
         self.leaf_stream = None
         self._leaf_on = False
         self._leaf_dirty = False
+        # Batch-chunk concurrency for the small encoder stages: the blocks of stage 3 / 4 are ~75 dependent launches
+        # of a few microseconds each on 312- / 78-token maps (launch-latency bound, most SMs idle).  Samples are
+        # independent through the whole encoder (GroupNorm is per sample), so the batch is cut into chunks whose
+        # block chains run on separate streams and overlap; they meet again at the stage boundary.  Parameter
+        # gradients of concurrent chunks accumulate atomically.  "stage:chunks" pairs, "" disables.
+        self.split = {}
+        for t in os.environ.get("CAMRADEPTH_SPLIT", "2:4,3:4").split(","):
+            if ":" in t:
+                a_, b_ = t.split(":")
+                self.split[int(a_)] = max(1, int(b_))
+        self.chunk_streams, self.chunk_leaf_streams = [], []
 
     def _timed(self, kind, name):
         if self.timed is None or (kind, name) not in self.timed:
@@ -222,6 +234,12 @@ class Engine:
             dst = torch.zeros(L["taps"] * L["cin_p"], L["cout_p"], dtype=dtype, device=self.device)
         ops.weight_pack(p.detach(), dst, self._cmap(name), L["cout"], L["cin"], L["taps"], L["cin_p"], L["cout_p"],
                         mode)
+        if self.chunk_streams:
+            # a pack launched lazily from one batch-chunk stream is read by the other chunks' streams as well
+            ev = torch.cuda.Event()
+            ev.record()
+            for st_ in self.chunk_streams:
+                st_.wait_event(ev)
         self._packs[key] = (dst, ver)
         self._pack_jobs[key] = ([(name, dst, self._cmap(name), L["cout"], L["cin"], L["taps"], L["cin_p"],
                                   L["cout_p"], mode)],
@@ -329,6 +347,28 @@ class Engine:
             torch.cuda.current_stream().wait_event(ev)
             self._leaf_dirty = False
 
+    def _chunks(self, s, B):
+        """[(b0, b1)] batch ranges of stage s (one range = no splitting)."""
+        n = min(self.split.get(s, 1), B, len(self.chunk_streams) if self.chunk_streams else 1)
+        if n <= 1 or self.tdtype != torch.bfloat16:
+            return [(0, B)]
+        step = (B + n - 1) // n
+        return [(b0, min(B, b0 + step)) for b0 in range(0, B, step)]
+
+    def _fork(self, n):
+        """Chunk streams 0..n-1 wait for everything launched so far on the current stream."""
+        ev = torch.cuda.Event()
+        ev.record()
+        for c in range(n):
+            self.chunk_streams[c].wait_event(ev)
+
+    def _join(self, n):
+        cur = torch.cuda.current_stream()
+        for c in range(n):
+            ev = torch.cuda.Event()
+            ev.record(self.chunk_streams[c])
+            cur.wait_event(ev)
+
     def conv_wgrad(self, x, dy, name, bias=None):
         with self._leaf():
             self._conv_wgrad(x, dy, name, bias)
@@ -389,21 +429,31 @@ class Engine:
 
     # ------------------------------------------------------------------ masks
     def make_masks(self, B):
+        """DropPath scales (two per block, in call order: attention branch, Mix-FFN branch; rate linspace(0, .1,
+        sum(depths)), simplified_attention.py:143-144,214) and Dropout2d(0.2) scale planes (CamRaDepth.py:96), all from
+        ONE Philox launch whose step counter lives on the device (fresh masks on every CUDA-graph replay)."""
         cfg = self.cfg
         nb = sum(cfg.depths)
-        rates = torch.linspace(0, DROP_PATH_RATE, nb).tolist()     # simplified_attention.py:214
-        # Block.forward calls self.drop_path twice (:143-144) and timm's drop_path draws an independent per-sample
-        # mask per call: two scales per block, in call order (attention branch, then Mix-FFN branch)
-        dps = []
-        for r in rates:
-            for _ in range(2):
-                if r == 0.0:
-                    dps.append(None)                                # Identity (:123)
-                else:
-                    keep = 1.0 - r
-                    dps.append((torch.rand(B, device=self.device) < keep).float() / keep)
-        d2s = [(torch.rand(B, MID, device=self.device) >= DROPOUT2D_P).float() / (1 - DROPOUT2D_P)
-               for _ in range(cfg.n_dropout_sites)]
+        rates = torch.linspace(0, DROP_PATH_RATE, nb).tolist()
+        n_dp, n_d2 = 2 * nb, cfg.n_dropout_sites
+        st = self._mask_state
+        if st is None or st["B"] != B or st["dev"] != self.device:
+            keep = torch.tensor([1.0 - r for r in rates for _ in range(2)], dtype=torch.float32).to(self.device)
+            seed = torch.initial_seed() & 0x7fffffffffffffff
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    seed = (seed + 0x9E3779B97F4A7C15 * (dist.get_rank() + 1)) & 0x7fffffffffffffff   # per-rank masks
+            except Exception:
+                pass
+            state = torch.tensor([seed, 0], dtype=torch.int64).to(self.device)
+            buf = torch.empty(n_dp * B + n_d2 * B * MID, dtype=torch.float32, device=self.device)
+            st = self._mask_state = dict(B=B, dev=self.device, keep=keep, state=state, buf=buf)
+        ops.make_masks(st["buf"], st["keep"], n_dp, B, n_d2, MID, 1.0 - DROPOUT2D_P, st["state"])
+        buf = st["buf"]
+        dps = [None if rates[i // 2] == 0.0 else buf[i * B:(i + 1) * B] for i in range(n_dp)]     # Identity (:123)
+        off = n_dp * B
+        d2s = [buf[off + j * B * MID: off + (j + 1) * B * MID].view(B, MID) for j in range(n_d2)]
         return dps, d2s
 
     # ------------------------------------------------------------------ encoder forward
@@ -728,21 +778,35 @@ class Engine:
             ops.argmax_map(lg, ncls, None, map_f32)
 
     # ------------------------------------------------------------------ whole forward
-    def forward(self, x, train, masks=None, save=True):
+    def forward(self, x, train, masks=None, save=True, packed=False):
+        """x: (B,cin,H,W) fp32 NCHW (the nn.Module surface), or with packed=True the engine's own input layout
+        (B,H,W,r8(cin)) bf16 NHWC as written by preprocess.pack_input_nhwc (no layout pack in the step)."""
         cfg = self.cfg
         if not x.is_cuda:
             raise RuntimeError("camradepth_b200 runs on CUDA devices only (no CPU fallback by design)")
+        if packed:
+            if self.tdtype != torch.bfloat16 or x.dtype != torch.bfloat16 or x.dim() != 4 or x.shape[-1] != r8(cfg.cin):
+                raise RuntimeError(f"packed input must be (B,H,W,{r8(cfg.cin)}) bf16 NHWC in bf16 mode")
+            x = x.detach().contiguous()
         if self.device != x.device:
             self.device = x.device
             self.fwd_arena = ZeroArena(self.device)
             self.bwd_arena = ZeroArena(self.device)
             self.leaf_stream = torch.cuda.Stream(self.device) if self.leaf_stages else None
-        B, cin, H, W = x.shape
+            nmax = max([1] + list(self.split.values()))
+            self.chunk_streams = [torch.cuda.Stream(self.device) for _ in range(nmax)] if nmax > 1 else []
+            self.chunk_leaf_streams = [torch.cuda.Stream(self.device) if self.leaf_stages else None
+                                       for _ in range(nmax)] if nmax > 1 else []
+        if packed:
+            (B, H, W, _), cin = x.shape, cfg.cin
+        else:
+            B, cin, H, W = x.shape
         if cin != cfg.cin:
             raise RuntimeError(f"expected {cfg.cin} input channels, got {cin}")
         if H % 32 or W % 32:
             raise RuntimeError(f"Sizes of tensors must match: H and W must be multiples of 32, got {H}x{W}")
-        x = x.detach().contiguous().float()
+        if not packed:
+            x = x.detach().contiguous().float()
         if save:
             # training forward: parameters may have been updated through `.data` (no version bump, e.g. the
             # reference's own optimizer), so packed copies are rebuilt every grad-enabled forward
@@ -760,8 +824,11 @@ class Engine:
         f32 = torch.float32
 
         # ---- encoder (SimplifiedTransformer.forward_features, simplified_attention.py:265-306)
-        X0 = self._zeros(B, H, W, r8(cin))
-        ops.nchw_to_nhwc(x, X0)
+        if packed:
+            X0 = x
+        else:
+            X0 = self._zeros(B, H, W, r8(cin))
+            ops.nchw_to_nhwc(x, X0)
         cur = X0
         stage_T, pe_recs, blk_recs = [], [], []
         bi = 0
@@ -769,15 +836,39 @@ class Engine:
             xr, prec = self.pe_fwd(s, cur, save)
             pe_recs.append(prec)
             brs = []
-            for i in range(cfg.depths[s]):
-                dp, dp_mlp = (None if m is None else m.to(self.device, f32).contiguous()
-                              for m in (dps[2 * bi], dps[2 * bi + 1]))
-                xr, brec = self.block_fwd(s, i, xr, dp, dp_mlp, save)
-                brs.append(brec)
-                bi += 1
-            blk_recs.append(brs)
+            chunks = self._chunks(s, B)
             st = self._empty(*xr.shape)
-            ops.scale_cast(xr, None, st)
+            if len(chunks) == 1:
+                for i in range(cfg.depths[s]):
+                    dp, dp_mlp = (None if m is None else m.to(self.device, f32).contiguous()
+                                  for m in (dps[2 * bi], dps[2 * bi + 1]))
+                    xr, brec = self.block_fwd(s, i, xr, dp, dp_mlp, save)
+                    brs.append(brec)
+                    bi += 1
+                ops.scale_cast(xr, None, st)
+            else:
+                # one stream per batch chunk; launches are issued block by block, round-robin over the chunks
+                masks_s = []
+                for i in range(cfg.depths[s]):
+                    masks_s.append(tuple(None if m is None else m.to(self.device, f32).contiguous()
+                                         for m in (dps[2 * bi], dps[2 * bi + 1])))
+                    bi += 1
+                xs = [xr[b0:b1] for (b0, b1) in chunks]
+                self._fork(len(chunks))
+                for i in range(cfg.depths[s]):
+                    recs_i = []
+                    for c, (b0, b1) in enumerate(chunks):
+                        dp, dp_mlp = (None if m is None else m[b0:b1] for m in masks_s[i])
+                        with torch.cuda.stream(self.chunk_streams[c]):
+                            xs[c], brec = self.block_fwd(s, i, xs[c], dp, dp_mlp, save)
+                        recs_i.append(brec)
+                    brs.append(recs_i)
+                for c, (b0, b1) in enumerate(chunks):
+                    with torch.cuda.stream(self.chunk_streams[c]):
+                        ops.scale_cast(xs[c], None, st[b0:b1])
+                self._join(len(chunks))
+                del xs
+            blk_recs.append(brs)
             stage_T.append(st)
             cur = st
         S.update(pe=pe_recs, blk=blk_recs, stage_T=stage_T)
@@ -821,7 +912,10 @@ class Engine:
         ops.nchw_to_nhwc(inter4, F4[..., MID:MID + 1])
 
         def skip_input(cat):
-            ops.nchw_to_nhwc(x, cat[..., MID + 1:MID + 1 + cin])
+            if packed:
+                ops.copy_channels(X0[..., :cin], cat[..., MID + 1:MID + 1 + cin])
+            else:
+                ops.nchw_to_nhwc(x, cat[..., MID + 1:MID + 1 + cin])
 
         F5 = self._feat(B, H, W, FW)
         S["D4"] = self.dec_fwd("depth_upsample.4", F4, skip_input, F5[..., :MID], d2[5 if seg else 4], save)
@@ -967,8 +1061,20 @@ class Engine:
             self._leaf_on = s in self.leaf_stages
             dx = torch.zeros(*stage_T[s].shape, dtype=f32, device=self.device)
             ops.add_f32(dx, dstage[s])
-            for i in reversed(range(cfg.depths[s])):
-                self.block_bwd(s, i, S["blk"][s][i], dx)
+            chunks = self._chunks(s, B)
+            if len(chunks) == 1:
+                for i in reversed(range(cfg.depths[s])):
+                    self.block_bwd(s, i, S["blk"][s][i], dx)
+            else:
+                main_leaf = self.leaf_stream
+                self._fork(len(chunks))
+                for i in reversed(range(cfg.depths[s])):
+                    for c, (b0, b1) in enumerate(chunks):
+                        self.leaf_stream = self.chunk_leaf_streams[c]
+                        with torch.cuda.stream(self.chunk_streams[c]):
+                            self.block_bwd(s, i, S["blk"][s][i][c], dx[b0:b1])
+                self.leaf_stream = main_leaf
+                self._join(len(chunks))
             self.pe_bwd(s, S["pe"][s], dx, dstage[s - 1] if s > 0 else None, True)
             self._leaf_on = False
             if s == 0:

@@ -28,7 +28,7 @@ class _Fn(torch.autograd.Function):
     def forward(ctx, model, x, *params):
         eng = model._engine_for(x)
         masks = model._pop_masks()
-        outs, saved = eng.forward(x, model.training, masks, save=True)
+        outs, saved = eng.forward(x, model.training, masks, save=True, packed=model._packed_call)
         ctx.model, ctx.eng, ctx.saved = model, eng, saved
         ret = [outs["final_depth"], outs["inter3"], outs["inter4"]]
         ctx.has_seg = outs["final_seg"] is not None
@@ -102,6 +102,7 @@ class CamRaDepth(nn.Module):
         self._masks = None
         self._grad_bucket_hook = None
         self._post_backward_hook = None
+        self._packed_call = False
 
     def _register(self, name, param):
         node = self
@@ -140,6 +141,16 @@ class CamRaDepth(nn.Module):
         m, self._masks = self._masks, None
         return m
 
+    def forward_packed(self, x_nhwc):
+        """Same as forward(x) for an input that is already in the engine's layout: (B,H,W,8) bf16 NHWC
+        [RGB | radar planes | zero pad] as produced by `preprocess.pack_input_nhwc` (the
+        GPU input pipeline feeds the network directly, no NCHW fp32 -> NHWC bf16 pack inside the step)."""
+        self._packed_call = True
+        try:
+            return self.forward(x_nhwc)
+        finally:
+            self._packed_call = False
+
     # -- reference surface -----------------------------------------------------------------------
     def forward(self, x):
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
@@ -155,7 +166,7 @@ class CamRaDepth(nn.Module):
                 unsup_map = res[i]
         else:
             eng = self._engine_for(x)
-            outs, _ = eng.forward(x, self.training, self._pop_masks(), save=False)
+            outs, _ = eng.forward(x, self.training, self._pop_masks(), save=False, packed=self._packed_call)
             final_depth, inter3, inter4 = outs["final_depth"], outs["inter3"], outs["inter4"]
             final_seg, unsup_map = outs["final_seg"], outs["unsup_map"]
         return {"depth": {"intermediate_depths": (None, None, inter3, inter4), "final_depth": final_depth},

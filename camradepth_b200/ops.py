@@ -65,6 +65,17 @@ def nhwc_to_nchw(src, dst):
     K.crd_nhwc_to_nchw(P(src), dcode(src), P(dst), B, C, H, W, _ld(src), stream())
 
 
+def copy_channels(src, dst):
+    """dst[..., :C] = src[..., :C] for channel-slice views of NHWC buffers (C = src.shape[-1], any alignment)."""
+    assert src.dtype == dst.dtype and src.shape == dst.shape
+    C = src.shape[-1]
+    K.crd_copy_channels(P(src), _ld(src), P(dst), _ld(dst), dcode(src), C, src.numel() // C, stream())
+
+
+def make_masks(out, keep_dp, n_dp, B, n_d2, C2, keep_d2, state):
+    K.crd_make_masks(P(out), P(keep_dp), n_dp, B, n_d2, C2, float(keep_d2), P(state), stream())
+
+
 # ------------------------------------------------------------------ conv
 def make_desc(x, y, Cin, Cout, KH, KW, stride, pad, transposed=0, act=0, accumulate=0, out_nchw=0,
               out_dtype=None, in_dtype=None, w_tap_stride=0, w_koff=0):

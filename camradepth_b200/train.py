@@ -77,6 +77,55 @@ class TrainStep:
         return {"loss_depth_final": out[0], "loss_depth_stage_4": out[1], "RMSE": out[2], "loss_seg": out[3]}
 
 
+def evaluate(model, batches, update_interval=None, max_depth=None, cutoff=600):
+    """`Trainer.eval` (src/main/runner.py:273-350) over an iterable of batch dicts
+    (image, gt_final, gt_s4, gt_seg as CUDA tensors) -> (val_loss, RMSE) with the reference's aggregation:
+    every `update_interval` batches (and on the last one) a window record [mean final-depth loss, mean stage-4 loss,
+    nan-mean of the last `cutoff` per-batch RMSEs, mean seg loss] is appended; the result is the nan-mean of the
+    records' first / third column.
+
+    Fixed here: the reference slices the input with `args.num_features`, a key its args never
+    define, so its eval loop raises AttributeError on the first batch (runner.py:297); the test loop uses
+    `args.input_channels` for the same purpose (:420) and so does this function.  The per-batch `.item()` host
+    syncs (:302-309) are gone: the four scalars of every batch stay on the device and are read back once.
+    The reference runs this forward under fp16 autocast; the engine's bf16 mode plays that role."""
+    import numpy as np
+    ui = int(update_interval if update_interval is not None else args.get("update_interval", 1))
+    md = float(args.get("max_depth", 100) if max_depth is None else max_depth)
+    crit_d, crit_s, mse = MaskedSmoothL1Loss(), MaskedFocalLoss(), MaskedMSELoss()
+    was_training = model.training
+    model.eval()
+    rows = []
+    with torch.no_grad():
+        for batch in batches:
+            x = batch["image"][:, :args.input_channels]
+            pred = model(x)
+            depth_full, inter = pred["depth"]["final_depth"], pred["depth"]["intermediate_depths"]
+            final_seg = pred["seg"]["final_seg"]
+            zero = torch.zeros((), dtype=torch.float32, device=depth_full.device)
+            l_seg = crit_s(final_seg, batch["gt_seg"]) if final_seg is not None else zero        # runner.py:301
+            l4 = crit_d(inter[-1].squeeze(1), batch["gt_s4"].squeeze(1))
+            lf = crit_d(depth_full, batch["gt_final"])
+            rmse = torch.sqrt(mse(depth_full, batch["gt_final"])) * md
+            rows.append(torch.stack([lf, l4, rmse, l_seg.reshape(())]))
+    model.train(was_training)
+    if not rows:
+        return float("nan"), float("nan")
+    vals = torch.stack(rows).double().cpu().numpy()             # ONE device -> host read
+    n = vals.shape[0]
+    eval_losses, rmse_arr, win = [], [], []
+    for i in range(n):
+        rmse_arr.append(vals[i, 2])
+        win.append(vals[i])
+        if (i + 1) % ui == 0 or (i + 1) == n:
+            w = np.array(win)
+            eval_losses.append([np.nanmean(w[:, 0]), np.nanmean(w[:, 1]), np.nanmean(rmse_arr[-cutoff:]),
+                                np.nanmean(w[:, 3])])
+            win = []
+    eval_losses = np.array(eval_losses)
+    return float(np.nanmean(eval_losses[:, 0])), float(np.nanmean(eval_losses[:, 2]))
+
+
 def save_checkpoint(path, model, optimizer, lr, steps):
     """Reference checkpoint layout (runner.py:369-371): {'state_dict','optimizer','lr','steps'}."""
     osd = optimizer.state_dict()

@@ -238,6 +238,28 @@ CRD_API int crd_minpool3x3s2(const float* x, float* y, int B, int H, int W, crd_
 CRD_API int crd_image_normalize(const unsigned char* img, float* out, int B, int H, int W, int Ctot,
                         const float* mean3, const float* std3, crd_stream_t stream);
 
+/* segmentation ground truth resized with nearest-neighbour sampling (dataloader.py:262-268: skimage resize, order 0,
+ * no anti-aliasing): dst[b][oh][ow] = src[b][floor((oh + .5) * Hi / Ho)][floor((ow + .5) * Wi / Wo)], int64 out;
+ * src is uint8 (src_is_u8 = 1) or int64. */
+CRD_API int crd_seg_resize_nearest(const void* src, int src_is_u8, long long* dst, int B, int Hi, int Wi, int Ho, int Wo,
+                           crd_stream_t stream);
+/* network input written directly in the engine's layout (NHWC bf16, ld channels per pixel, multiple of 8):
+ * [ImageNet-normalised RGB from the uint8 HWC image | Ce <= 5 fp32 planes of extra (B,Ce,H,W) | zeros].
+ * Removes the NCHW fp32 -> NHWC bf16 pack of the nn.Module boundary.  mean3 / std3 are HOST pointers. */
+CRD_API int crd_pack_input_nhwc(const unsigned char* img, const float* extra, void* dst, int B, int H, int W, int Ce,
+                        int ld, const float* mean3, const float* std3, crd_stream_t stream);
+/* dst[pix][0..C) = src[pix][0..C) for every pixel: a (small, arbitrarily aligned) channel slice of one NHWC buffer
+ * into a channel slice of another (the network input into the full-resolution concat buffers, CamRaDepth.py:146,163) */
+CRD_API int crd_copy_channels(const void* src, int ld_src, void* dst, int ld_dst, int dtype, int C, long long npix,
+                      crd_stream_t stream);
+/* Stochastic masks of one training forward in ONE launch: timm DropPath scales (one per drop_path CALL: n_dp rows of
+ * B values, keep probability keep_dp[row]; simplified_attention.py:143-144) followed by n_d2 Dropout2d scale planes
+ * of B*C2 values (keep probability keep_d2; CamRaDepth.py:96).  Value = 1/keep with probability keep, else 0.
+ * Philox4x32-10 keyed by state[0] (seed) and state[1] (step counter, advanced by the kernel: CUDA-graph replays
+ * draw fresh masks).  state is DEVICE memory. */
+CRD_API int crd_make_masks(float* out, const float* keep_dp, int n_dp, int B, int n_d2, int C2, float keep_d2,
+                   unsigned long long* state, crd_stream_t stream);
+
 /* ---------------------------------------------------------------- diffGradNorm (diffGradNorm.py:41-113)
  * multi-tensor: table rows describe (param, grad, exp_avg, exp_avg_sq, previous_grad, numel). */
 typedef struct {

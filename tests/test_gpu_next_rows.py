@@ -169,3 +169,124 @@ def test_checkpoint_layout_roundtrip(tmp_path):
     m2 = C.CamRaDepth(precision="bf16")
     C.load_checkpoint_with_shape_match(m2, {"module." + k: v for k, v in ck["state_dict"].items()})
     assert all(torch.equal(a.cpu(), b2) for a, b2 in zip(m.state_dict().values(), m2.state_dict().values()))
+
+
+def test_seg_label_resize_matches_skimage_rule():
+    """dataloader.py:262-268: skimage.transform.resize(order=0, anti_aliasing=False) = scipy.ndimage.zoom(order=0,
+    grid_mode=True) (skimage is not in this image; scipy is what it calls)."""
+    import numpy as np
+    from scipy import ndimage
+    from camradepth_b200.preprocess import seg_resize_nearest
+    rng = np.random.default_rng(0)
+    for (hi, wi, ho, wo) in [(416, 800, 208, 400), (416, 800, 416, 800), (450, 800, 192, 416), (37, 53, 64, 96)]:
+        lab = rng.integers(0, 21, size=(2, hi, wi)).astype(np.uint8)
+        lab[rng.random(lab.shape) < 0.1] = 255
+        ref = np.stack([ndimage.zoom(l, (ho / hi, wo / wi), order=0, mode="reflect", grid_mode=True) for l in lab])
+        for t in (torch.from_numpy(lab), torch.from_numpy(lab.astype(np.int64))):
+            out = seg_resize_nearest(t.to(dev), (ho, wo))
+            assert out.dtype == torch.int64 and tuple(out.shape) == (2, ho, wo)
+            assert np.array_equal(out.cpu().numpy(), ref.astype(np.int64)), (hi, wi, ho, wo)
+
+
+def test_packed_input_feed_matches_module_surface():
+    """GPU input pipeline feeding the engine layout directly: forward_packed(pack_input_nhwc(...))
+    == forward(NCHW fp32 tensor built by normalize_image + radar planes)."""
+    import camradepth_b200 as C
+    from camradepth_b200.preprocess import normalize_image, pack_input_nhwc
+    C.set_model("base")
+    torch.manual_seed(0)
+    m = C.CamRaDepth(precision="bf16").cuda().eval()
+    B, H, W = 2, 64, 96
+    img = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=dev)
+    radar = torch.rand(B, 4, H, W, device=dev) * (torch.rand(B, 1, H, W, device=dev) < 0.05)
+    x = torch.zeros(B, 7, H, W, device=dev)
+    normalize_image(img, x)
+    x[:, 3:] = radar
+    xp = pack_input_nhwc(img, radar.contiguous())
+    assert xp.shape == (B, H, W, 8) and xp.dtype == torch.bfloat16
+    assert rel(xp[..., :7].float().permute(0, 3, 1, 2), x) < 4e-3 and float(xp[..., 7].abs().max()) == 0
+    with torch.no_grad():
+        a = m(x)["depth"]["final_depth"]
+        b = m.forward_packed(xp)["depth"]["final_depth"]
+    assert rel(b, a) < 5e-3          # same bf16 input values; GroupNorm sums are atomics-ordered
+    # gradients flow through the packed entry too
+    m.train(False)
+    loss = C.MaskedSmoothL1Loss()(m.forward_packed(xp)["depth"]["final_depth"], torch.rand(B, 1, H, W, device=dev))
+    loss.backward()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
+    with pytest.raises(RuntimeError):
+        m.forward_packed(xp.float())
+
+
+def test_stochastic_masks_kernel():
+    """One Philox launch for all DropPath / Dropout2d scales: values in {0, 1/keep}, keep rates honoured, rate-0
+    calls are identity, and the device-side step counter gives fresh masks per call (CUDA-graph replays included)."""
+    from camradepth_b200 import ops
+    n_dp, B, n_d2, C2 = 68, 64, 7, 128
+    rates = torch.linspace(0, 0.1, n_dp // 2).repeat_interleave(2)
+    keep = (1 - rates).to(dev)
+    out = torch.empty(n_dp * B + n_d2 * B * C2, device=dev)
+    state = torch.tensor([1234, 0], dtype=torch.int64, device=dev)
+    draws = []
+    for it in range(200):
+        ops.make_masks(out, keep, n_dp, B, n_d2, C2, 0.8, state)
+        draws.append(out.clone())
+    torch.cuda.synchronize()
+    assert int(state[1]) == 200
+    d = torch.stack(draws)
+    dp = d[:, :n_dp * B].view(200, n_dp, B)
+    d2 = d[:, n_dp * B:]
+    assert bool((dp[:, :2] == 1).all())                                   # rate 0: never dropped
+    for r in (10, 40, 67):
+        k = float(keep[r])
+        vals = dp[:, r].unique()
+        assert all(abs(float(v)) < 1e-6 or abs(float(v) - 1 / k) < 1e-5 for v in vals)
+        frac = float((dp[:, r] > 0).float().mean())
+        assert abs(frac - k) < 0.02, (r, frac, k)
+    assert abs(float((d2 > 0).float().mean()) - 0.8) < 5e-3
+    assert set(d2.unique().tolist()) <= {0.0, 1.25}
+    assert not torch.equal(draws[0], draws[1])
+    # same seed and counter -> same masks (reproducible)
+    state2 = torch.tensor([1234, 0], dtype=torch.int64, device=dev)
+    out2 = torch.empty_like(out)
+    ops.make_masks(out2, keep, n_dp, B, n_d2, C2, 0.8, state2)
+    assert torch.equal(out2, draws[0])
+
+
+def test_eval_loop_matches_reference_semantics():
+    """`evaluate` against the reference's eval loop (runner.py:273-350) restated on the CPU oracle, with the F12 fix
+    (input sliced with args.input_channels): five batches, update_interval 2, fp32 mode."""
+    import numpy as np
+    import camradepth_b200 as C
+    from camradepth_b200.synthetic import make_batch
+    from oracle import camradepth_oracle as O
+    torch.set_num_threads(os.cpu_count() or 8)
+    cfg = O.Cfg("supervised_seg")
+    sd = O.init_state_dict(cfg, seed=3, perturb=0.02)
+    C.set_model("supervised_seg")
+    try:
+        model = C.CamRaDepth(precision="fp32")
+        model.load_state_dict(sd)
+        model = model.to(dev).train()             # evaluate() must switch to eval and restore the mode
+        batches = [make_batch(1, 64, 64, seed=40 + i) for i in range(5)]
+        batches[3]["gt_final"] = torch.zeros_like(batches[3]["gt_final"])       # empty mask -> NaN losses (nanmean)
+        val_loss, rmse = C.evaluate(model, [{k: v.to(dev) for k, v in b.items()} for b in batches], update_interval=2)
+        assert model.training
+        # reference loop
+        eval_losses, rmse_arr, fin, s4, seg = [], [], [], [], []
+        with torch.no_grad():
+            for i, b in enumerate(batches):
+                pred = O.forward(sd, cfg, b["image"][:, :cfg.cin])
+                seg.append(float(O.masked_focal(pred["seg"]["final_seg"], b["gt_seg"])))
+                s4.append(float(O.masked_smooth_l1(pred["depth"]["intermediate_depths"][-1].squeeze(1), b["gt_s4"].squeeze(1))))
+                fin.append(float(O.masked_smooth_l1(pred["depth"]["final_depth"], b["gt_final"])))
+                rmse_arr.append(float(torch.sqrt(O.masked_mse(pred["depth"]["final_depth"], b["gt_final"]))) * 100)
+                if (i + 1) % 2 == 0 or (i + 1) == len(batches):
+                    eval_losses.append([np.nanmean(fin), np.nanmean(s4), np.nanmean(rmse_arr[-600:]), np.nanmean(seg)])
+                    fin, s4, seg = [], [], []
+        eval_losses = np.array(eval_losses)
+        want_loss, want_rmse = np.nanmean(eval_losses[:, 0]), np.nanmean(eval_losses[:, 2])
+        assert abs(val_loss - want_loss) < 1e-4 * abs(want_loss), (val_loss, want_loss)
+        assert abs(rmse - want_rmse) < 1e-4 * abs(want_rmse), (rmse, want_rmse)
+    finally:
+        C.set_model("base")

@@ -29,6 +29,11 @@ step)   timeout 300 python tools/profile_step.py --batch 32 > gpurun_out/${TAG}_
 convs)  timeout 300 python tools/profile_convs.py 32 > gpurun_out/${TAG}_conv_profile.txt 2>&1; tail -30 gpurun_out/${TAG}_conv_profile.txt ;;
 ew)     timeout 300 python tools/bench_elementwise.py > gpurun_out/${TAG}_elementwise.txt 2>&1 ;;
 configs) timeout 900 python tools/bench_configs.py > gpurun_out/${TAG}_bench_configs.jsonl 2> gpurun_out/${TAG}_bench_configs.err; cat gpurun_out/${TAG}_bench_configs.jsonl ;;
+ab)     # A/B of engine switches: AB="CAMRADEPTH_SPLIT=;CAMRADEPTH_LEAF_STAGES=" -> one quick bench line per setting
+        echo "${AB}" | tr ';' '\n' | while read -r kv; do
+          echo "== ${kv:-default}" >> gpurun_out/${TAG}_ab.txt
+          env ${kv} timeout 600 python bench.py --quick --steps 10 --warmup 3 >> gpurun_out/${TAG}_ab.txt 2>/dev/null
+        done; cat gpurun_out/${TAG}_ab.txt ;;
 dp2)    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_check.py supervised_seg fp32 > gpurun_out/${TAG}_dp_check.txt 2>&1; tail -4 gpurun_out/${TAG}_dp_check.txt
         timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/dp_check.py base bf16 >> gpurun_out/${TAG}_dp_check.txt 2>&1; tail -3 gpurun_out/${TAG}_dp_check.txt ;;
 benchN) N=${NGPU:-2}; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N > gpurun_out/${TAG}_bench_${N}gpu.json 2> gpurun_out/${TAG}_bench_${N}gpu.err; tail -c 1500 gpurun_out/${TAG}_bench_${N}gpu.json; tail -5 gpurun_out/${TAG}_bench_${N}gpu.err ;;
