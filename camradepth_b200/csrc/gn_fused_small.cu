@@ -1,0 +1,332 @@
+// GroupNorm (+GELU, +Dropout2d scale) forward and backward in ONE launch each, for the encoder-sized tensors.
+//
+// The three-step protocol of norm_act.cu (per-(b,c) sums -> finalize -> apply; backward: reduce -> finalize ->
+// apply) costs three launches per GroupNorm and direction.  The encoder has 165 GroupNorms per step on tensors of
+// 0.1 .. 80 MB whose kernels are a few microseconds each, so the step pays ~1000 launches of fixed cost for them
+// (measured: gn_finalize 4.2 us, gn_bwd_finalize 5.0 us per launch for a few hundred bytes of work).  Here one CTA
+// owns a (sample, channel tile of whole groups) slab [N pixels][CT channels] and sweeps it twice: sweep 1 reduces
+// (the second read of the slab is an L2 hit: these tensors fit the 126 MB L2), the statistics are finalised inside
+// the CTA (shared memory, fp64 for the mean / variance), sweep 2 applies.  Same arithmetic as the three-step path.
+//   forward : y = act(a*x + b) * post,   a = gamma*rstd, b = beta - mean*a        (utils.py:223-228,
+//             simplified_attention.py:36-38,141-145,184-187); optionally the sums come from the producing conv's
+//             read-out (sums_in) and sweep 1 is skipped; ab / mean_rstd / xbar are written for the backward pass
+//   backward: dz = (dy + addbc) * post * act'(a*x+b);  dx (+)= A*dz + Bq*x + Cq;  dgamma/dbeta += ...
+#include "common.cuh"
+#include "../../include/camradepth_b200.h"
+
+namespace {
+
+constexpr int GF_THREADS = 256;
+
+__device__ __forceinline__ float gf_act_fwd(float z, int act) {
+  if (act == CRD_ACT_GELU) return gelu_f(z);
+  if (act == CRD_ACT_SIGMOID) return sigmoid_f(z);
+  return z;
+}
+__device__ __forceinline__ float gf_act_bwd(float z, int act) {
+  if (act == CRD_ACT_GELU) return gelu_grad_f(z);
+  if (act == CRD_ACT_SIGMOID) { const float s = sigmoid_f(z); return s * (1.f - s); }
+  return 1.f;
+}
+
+struct GfGeom {
+  int B, C, G, cpg, CT, cvec, rows;
+  long long N;
+};
+
+// per-thread partial sums -> per-channel totals in shared memory: red[0][c], red[1][c]
+__device__ __forceinline__ void gf_block_reduce(const float (&s0)[8], const float (&s1)[8], float* part /*[rows][CT][2]*/,
+                                                float* tot /*[2][CT]*/, int tx, int ty, int CT, int rows) {
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    part[(ty * CT + tx * 8 + j) * 2 + 0] = s0[j];
+    part[(ty * CT + tx * 8 + j) * 2 + 1] = s1[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * CT; c += GF_THREADS) {
+    const int ch = c >> 1, q = c & 1;
+    float a = 0.f;
+    for (int r = 0; r < rows; r++) a += part[(r * CT + ch) * 2 + q];
+    tot[q * CT + ch] = a;
+  }
+  __syncthreads();
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(GF_THREADS)
+gn_fused_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ sums_in, const float* __restrict__ post,
+                    int act, float* __restrict__ ab_out, float* __restrict__ mr_out, float* __restrict__ xbar_out,
+                    GfGeom g, int ldx, int ldy, float eps) {
+  extern __shared__ float sm[];
+  float* part = sm;                                   // [rows][CT][2]
+  float* tot = part + g.rows * g.CT * 2;              // [2][CT]
+  float* coef = tot + 2 * g.CT;                       // [2][CT]: a, b
+  const int tx = threadIdx.x % g.cvec, ty = threadIdx.x / g.cvec;
+  const int b = blockIdx.y, c0 = blockIdx.x * g.CT, c = c0 + tx * 8;
+  const TI* xb = x + (long long)b * g.N * ldx + c;
+  if (sums_in == nullptr) {
+    float s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { s0[j] = 0.f; s1[j] = 0.f; }
+    constexpr int U = 4;
+    for (long long p = ty; p < g.N; p += (long long)U * g.rows) {
+      typename Raw8<TI>::type raw[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const long long q = p + (long long)u * g.rows;
+        raw[u] = ldg16(xb + (q < g.N ? q : p) * ldx);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (p + (long long)u * g.rows >= g.N) break;
+        float v[8];
+        unpack8(raw[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; j++) { s0[j] += v[j]; s1[j] = fmaf(v[j], v[j], s1[j]); }
+      }
+    }
+    gf_block_reduce(s0, s1, part, tot, tx, ty, g.CT, g.rows);
+  } else {
+    for (int i = threadIdx.x; i < 2 * g.CT; i += GF_THREADS) {
+      const int ch = i >> 1, q = i & 1;
+      tot[q * g.CT + ch] = sums_in[((long long)b * g.C + c0 + ch) * 2 + q];
+    }
+    __syncthreads();
+  }
+  // finalize: one thread per group of this tile
+  const int gpt = g.CT / g.cpg;
+  if (threadIdx.x < gpt) {
+    double s = 0.0, ss = 0.0;
+    for (int j = 0; j < g.cpg; j++) { s += (double)tot[threadIdx.x * g.cpg + j]; ss += (double)tot[g.CT + threadIdx.x * g.cpg + j]; }
+    const double cnt = (double)g.cpg * (double)g.N;
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const int gi = c0 / g.cpg + threadIdx.x;
+    if (mr_out) { mr_out[((long long)b * g.G + gi) * 2] = (float)mean; mr_out[((long long)b * g.G + gi) * 2 + 1] = rstd; }
+    for (int j = 0; j < g.cpg; j++) {
+      const int ch = threadIdx.x * g.cpg + j;
+      const float a = gamma[c0 + ch] * rstd;
+      const float bb = beta[c0 + ch] - (float)mean * a;
+      coef[ch] = a; coef[g.CT + ch] = bb;
+      if (ab_out) { ab_out[((long long)b * g.C + c0 + ch) * 2] = a; ab_out[((long long)b * g.C + c0 + ch) * 2 + 1] = bb; }
+      if (xbar_out) xbar_out[(long long)b * g.C + c0 + ch] = a * (tot[ch] / (float)g.N) + bb;
+    }
+  }
+  __syncthreads();
+  if (y == nullptr) return;
+  float a[8], sh[8], ps[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    a[j] = coef[tx * 8 + j];
+    sh[j] = coef[g.CT + tx * 8 + j];
+    ps[j] = post ? post[(long long)b * g.C + c + j] : 1.f;
+  }
+  TO* yb = y + (long long)b * g.N * ldy + c;
+  constexpr int U = 4;
+  for (long long p = ty; p < g.N; p += (long long)U * g.rows) {
+    typename Raw8<TI>::type raw[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long q = p + (long long)u * g.rows;
+      raw[u] = ldg16(xb + (q < g.N ? q : p) * ldx);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long q = p + (long long)u * g.rows;
+      if (q >= g.N) break;
+      float v[8];
+      unpack8(raw[u], v);
+      if (act == CRD_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = gelu_f(fmaf(a[j], v[j], sh[j])) * ps[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = gf_act_fwd(fmaf(a[j], v[j], sh[j]), act) * ps[j];
+      }
+      store8(yb + q * ldy, v);
+    }
+  }
+}
+
+template <typename TD, typename TX, typename TO>
+__global__ void __launch_bounds__(GF_THREADS)
+gn_fused_bwd_kernel(TD* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ ab,
+                    const float* __restrict__ mean_rstd, const float* __restrict__ gamma, const float* __restrict__ post,
+                    const float* __restrict__ addbc, int act, TO* __restrict__ dx, int accumulate, float* dgamma,
+                    float* dbeta, GfGeom g, int lddy, int ldx, int lddx) {
+  extern __shared__ float sm[];
+  float* part = sm;
+  float* tot = part + g.rows * g.CT * 2;              // [2][CT]: sum dz, sum dz*x
+  float* coef = tot + 2 * g.CT;                       // [3][CT]: A, Bq, Cq
+  const int tx = threadIdx.x % g.cvec, ty = threadIdx.x / g.cvec;
+  const int b = blockIdx.y, c0 = blockIdx.x * g.CT, c = c0 + tx * 8;
+  float a[8], sh[8], k1[8], k0[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const long long bc = (long long)b * g.C + c + j;
+    a[j] = ab[bc * 2];
+    sh[j] = ab[bc * 2 + 1];
+    const float ps = post ? post[bc] : 1.f, ad = addbc ? addbc[bc] : 0.f;
+    k1[j] = ps; k0[j] = ad * ps;                      // dz = (k1*dy + k0) * act'(z)
+  }
+  TD* dyb = dy + (long long)b * g.N * lddy + c;
+  const TX* xb = x + (long long)b * g.N * ldx + c;
+  const bool inplace = act != CRD_ACT_NONE;           // dz replaces dy, so act' is evaluated once (dy is consumed here)
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) { s0[j] = 0.f; s1[j] = 0.f; }
+  constexpr int U = 4;
+  for (long long p = ty; p < g.N; p += (long long)U * g.rows) {
+    typename Raw8<TD>::type rg[U];
+    typename Raw8<TX>::type rx[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long q = p + (long long)u * g.rows;
+      const long long qq = q < g.N ? q : p;
+      rg[u] = ldg16(dyb + qq * lddy);
+      rx[u] = ldg16(xb + qq * ldx);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long q = p + (long long)u * g.rows;
+      if (q >= g.N) break;
+      float gd[8], v[8];
+      unpack8(rg[u], gd);
+      unpack8(rx[u], v);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        float dz = fmaf(k1[j], gd[j], k0[j]);
+        if (act == CRD_ACT_GELU) dz *= gelu_grad_f(fmaf(a[j], v[j], sh[j]));
+        else if (act != CRD_ACT_NONE) dz *= gf_act_bwd(fmaf(a[j], v[j], sh[j]), act);
+        gd[j] = dz;
+        s0[j] += dz;
+        s1[j] = fmaf(dz, v[j], s1[j]);
+      }
+      if (inplace) store8(dyb + q * lddy, gd);
+    }
+  }
+  gf_block_reduce(s0, s1, part, tot, tx, ty, g.CT, g.rows);
+  const int gpt = g.CT / g.cpg;
+  if (threadIdx.x < gpt) {
+    const int gi = c0 / g.cpg + threadIdx.x;
+    const float mu = mean_rstd[((long long)b * g.G + gi) * 2], r = mean_rstd[((long long)b * g.G + gi) * 2 + 1];
+    double t1 = 0.0, t2 = 0.0;
+    for (int j = 0; j < g.cpg; j++) {
+      const int ch = threadIdx.x * g.cpg + j;
+      const double ga = (double)gamma[c0 + ch];
+      t1 += ga * (double)tot[ch];
+      t2 += ga * ((double)tot[g.CT + ch] - (double)mu * (double)tot[ch]);
+    }
+    const double m = (double)g.cpg * (double)g.N;
+    const float m1 = (float)(t1 / m), m2 = (float)((double)r * t2 / m);
+    for (int j = 0; j < g.cpg; j++) {
+      const int ch = threadIdx.x * g.cpg + j;
+      coef[ch] = r * gamma[c0 + ch];
+      coef[g.CT + ch] = -r * r * m2;
+      coef[2 * g.CT + ch] = -r * m1 + r * r * m2 * mu;
+      if (dgamma) atomicAdd(dgamma + c0 + ch, r * (tot[g.CT + ch] - mu * tot[ch]));
+      if (dbeta) atomicAdd(dbeta + c0 + ch, tot[ch]);
+    }
+  }
+  __syncthreads();
+  float cA[8], cB[8], cC[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    cA[j] = coef[tx * 8 + j];
+    cB[j] = coef[g.CT + tx * 8 + j];
+    cC[j] = coef[2 * g.CT + tx * 8 + j];
+  }
+  if (inplace) __threadfence_block();                 // this thread re-reads only what it wrote itself
+  TO* dxb = dx + (long long)b * g.N * lddx + c;
+  for (long long p = ty; p < g.N; p += (long long)U * g.rows) {
+    typename Raw8<TD>::type rg[U];
+    typename Raw8<TX>::type rx[U];
+    typename Raw8<TO>::type ro[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long q = p + (long long)u * g.rows;
+      const long long qq = q < g.N ? q : p;
+      rg[u] = ldg16(dyb + qq * lddy);
+      rx[u] = ldg16(xb + qq * ldx);
+      if (accumulate) ro[u] = ldg16(dxb + qq * lddx);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long q = p + (long long)u * g.rows;
+      if (q >= g.N) break;
+      float gd[8], v[8], o[8];
+      unpack8(rg[u], gd);
+      unpack8(rx[u], v);
+      if (accumulate) unpack8(ro[u], o);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float dz = inplace ? gd[j] : fmaf(k1[j], gd[j], k0[j]);
+        const float rr = fmaf(cA[j], dz, fmaf(cB[j], v[j], cC[j]));
+        o[j] = accumulate ? o[j] + rr : rr;
+      }
+      store8(dxb + q * lddx, o);
+    }
+  }
+}
+
+// channel tile: whole groups, at least 32 channels (64 .. 128-byte rows) when the channel count allows
+inline bool gf_geom(int B, long long N, int C, int G, GfGeom& g) {
+  if (G <= 0 || C % G) return false;
+  const int cpg = C / G;
+  if (cpg % 8 || cpg > 256) return false;
+  int CT = cpg;
+  while (CT < 32 && C % (CT * 2) == 0) CT *= 2;
+  if (CT / 8 > GF_THREADS) return false;
+  g.B = B; g.C = C; g.G = G; g.cpg = cpg; g.CT = CT; g.cvec = CT / 8; g.rows = GF_THREADS / g.cvec; g.N = N;
+  return GF_THREADS % g.cvec == 0;
+}
+inline size_t gf_smem(const GfGeom& g, int ncoef) { return (size_t)(g.rows * g.CT * 2 + 2 * g.CT + ncoef * g.CT) * sizeof(float); }
+
+}  // namespace
+
+extern "C" int crd_gn_fused_supported(int B, long long N, int C, int G) {
+  GfGeom g;
+  return gf_geom(B, N, C, G, g) ? 1 : 0;
+}
+
+extern "C" int crd_gn_fused_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta,
+                                const float* sums_in, const float* post, int act, float* ab_out, float* mean_rstd_out,
+                                float* xbar_out, int B, long long N, int C, int G, int ldx, int ldy, float eps,
+                                crd_stream_t stream) {
+  GfGeom g;
+  CRD_REQUIRE(gf_geom(B, N, C, G, g));
+  CRD_REQUIRE(ldx % 8 == 0 && (y == nullptr || ldy % 8 == 0) && gamma && beta);
+  CRD_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0);
+  if ((long long)B * N == 0) return 0;
+  const dim3 grid(C / g.CT, B);
+  const size_t smem = gf_smem(g, 2);
+  cudaStream_t s = (cudaStream_t)stream;
+  CRD_DISPATCH_1(x_dtype, TI, CRD_DISPATCH_1(y_dtype, TO, gn_fused_fwd_kernel<TI, TO><<<grid, GF_THREADS, smem, s>>>(
+                                  (const TI*)x, (TO*)y, gamma, beta, sums_in, post, act, ab_out, mean_rstd_out, xbar_out,
+                                  g, ldx, ldy, eps)));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int crd_gn_fused_bwd(void* dy, int dy_dtype, const void* x, int x_dtype, const float* ab,
+                                const float* mean_rstd, const float* gamma, const float* post, const float* addbc,
+                                int act, void* dx, int dx_dtype, int accumulate, float* dgamma, float* dbeta, int B,
+                                long long N, int C, int G, int lddy, int ldx, int lddx, crd_stream_t stream) {
+  GfGeom g;
+  CRD_REQUIRE(gf_geom(B, N, C, G, g));
+  CRD_REQUIRE(lddy % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0 && ab && mean_rstd && gamma && dx);
+  CRD_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0);
+  if ((long long)B * N == 0) return 0;
+  const dim3 grid(C / g.CT, B);
+  const size_t smem = gf_smem(g, 3);
+  cudaStream_t s = (cudaStream_t)stream;
+  CRD_DISPATCH_1(dy_dtype, TD, CRD_DISPATCH_1(x_dtype, TX, CRD_DISPATCH_1(dx_dtype, TO,
+      gn_fused_bwd_kernel<TD, TX, TO><<<grid, GF_THREADS, smem, s>>>((TD*)dy, (const TX*)x, ab, mean_rstd, gamma, post, addbc,
+                                                                    act, (TO*)dx, accumulate, dgamma, dbeta, g, lddy, ldx,
+                                                                    lddx))));
+  CRD_LAUNCH_CHECK();
+  return 0;
+}

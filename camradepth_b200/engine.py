@@ -15,7 +15,6 @@ Data layout in HBM (bf16 mode; fp32 mode stores everything as fp32):
 """
 from __future__ import annotations
 
-import contextlib
 import math
 import os
 
@@ -90,35 +89,19 @@ class Engine:
         self.use_tc_wgrad = self.use_tc and os.environ.get("CAMRADEPTH_TC_WGRAD", "1") == "1"
         # GroupNorm statistics from the accumulator read-out of the producing tcgen05 conv / GEMM
         self.fuse_gn_stats = self.use_tc and os.environ.get("CAMRADEPTH_GN_EPILOGUE", "1") == "1"
+        # GroupNorm passes whose tensors total at most this many bytes run as ONE launch (two sweeps of an
+        # L2-resident slab per CTA) instead of statistics / finalize / apply launches; 0 disables
+        self.gn_fused_bytes = int(float(os.environ.get("CAMRADEPTH_GN_FUSED_MB", "64")) * (1 << 20))
         self._build_layers()
         self.fwd_arena = None
         self.bwd_arena = None
         # optional CUDA-event timing of selected conv launches: {(kind, weight name): [(ev0, ev1), ...]}
         self.timed = None
+        self.timed_flops = {}        # (kind, weight name) -> MACs*2 of the launch actually timed, where it differs from the layer's own
         self._grad_epoch = 0
         self._flat_own = None
         self._grads_out = None
         self._mask_state = None
-        # Gradient leaves (weight / bias gradients: nothing later in the backward program reads them) of the listed
-        # encoder stages run on a second stream, concurrently with the data-gradient chain.  The kernels of stages
-        # 3 / 4 occupy a fraction of the GPU each (20 .. 312 CTAs), so two streams fill SMs that one leaves idle.
-        # Joined at the end of every block (before its temporaries are released).  "" disables.
-        ls = os.environ.get("CAMRADEPTH_LEAF_STAGES", "2,3")
-        self.leaf_stages = tuple(int(t) for t in ls.split(",") if t.strip() != "")
-        self.leaf_stream = None
-        self._leaf_on = False
-        self._leaf_dirty = False
-        # Batch-chunk concurrency for the small encoder stages: the blocks of stage 3 / 4 are ~75 dependent launches
-        # of a few microseconds each on 312- / 78-token maps (launch-latency bound, most SMs idle).  Samples are
-        # independent through the whole encoder (GroupNorm is per sample), so the batch is cut into chunks whose
-        # block chains run on separate streams and overlap; they meet again at the stage boundary.  Parameter
-        # gradients of concurrent chunks accumulate atomically.  "stage:chunks" pairs, "" disables.
-        self.split = {}
-        for t in os.environ.get("CAMRADEPTH_SPLIT", "2:4,3:4").split(","):
-            if ":" in t:
-                a_, b_ = t.split(":")
-                self.split[int(a_)] = max(1, int(b_))
-        self.chunk_streams, self.chunk_leaf_streams = [], []
 
     def _timed(self, kind, name):
         if self.timed is None or (kind, name) not in self.timed:
@@ -234,12 +217,6 @@ class Engine:
             dst = torch.zeros(L["taps"] * L["cin_p"], L["cout_p"], dtype=dtype, device=self.device)
         ops.weight_pack(p.detach(), dst, self._cmap(name), L["cout"], L["cin"], L["taps"], L["cin_p"], L["cout_p"],
                         mode)
-        if self.chunk_streams:
-            # a pack launched lazily from one batch-chunk stream is read by the other chunks' streams as well
-            ev = torch.cuda.Event()
-            ev.record()
-            for st_ in self.chunk_streams:
-                st_.wait_event(ev)
         self._packs[key] = (dst, ver)
         self._pack_jobs[key] = ([(name, dst, self._cmap(name), L["cout"], L["cin"], L["taps"], L["cin_p"],
                                   L["cout_p"], mode)],
@@ -329,51 +306,7 @@ class Engine:
         if ev is not None:
             ev.record()
 
-    def _leaf(self):
-        """Context for launching a gradient leaf: the side stream, ordered after everything launched so far."""
-        if not self._leaf_on or self.leaf_stream is None:
-            return contextlib.nullcontext()
-        ev = torch.cuda.Event()
-        ev.record()
-        self.leaf_stream.wait_event(ev)
-        self._leaf_dirty = True
-        return torch.cuda.stream(self.leaf_stream)
-
-    def _leaf_join(self):
-        """The main stream waits for the leaves launched since the last join."""
-        if self._leaf_dirty:
-            ev = torch.cuda.Event()
-            ev.record(self.leaf_stream)
-            torch.cuda.current_stream().wait_event(ev)
-            self._leaf_dirty = False
-
-    def _chunks(self, s, B):
-        """[(b0, b1)] batch ranges of stage s (one range = no splitting)."""
-        n = min(self.split.get(s, 1), B, len(self.chunk_streams) if self.chunk_streams else 1)
-        if n <= 1 or self.tdtype != torch.bfloat16:
-            return [(0, B)]
-        step = (B + n - 1) // n
-        return [(b0, min(B, b0 + step)) for b0 in range(0, B, step)]
-
-    def _fork(self, n):
-        """Chunk streams 0..n-1 wait for everything launched so far on the current stream."""
-        ev = torch.cuda.Event()
-        ev.record()
-        for c in range(n):
-            self.chunk_streams[c].wait_event(ev)
-
-    def _join(self, n):
-        cur = torch.cuda.current_stream()
-        for c in range(n):
-            ev = torch.cuda.Event()
-            ev.record(self.chunk_streams[c])
-            cur.wait_event(ev)
-
     def conv_wgrad(self, x, dy, name, bias=None):
-        with self._leaf():
-            self._conv_wgrad(x, dy, name, bias)
-
-    def _conv_wgrad(self, x, dy, name, bias=None):
         L = self.L[name]
         direct = L["taps"] == 1 and L["cmap"] is None and L["cin_p"] == L["cin"]
         g = self.pg[name]
@@ -399,21 +332,40 @@ class Engine:
         if db is not None:
             ops.col_sum(dy, db, L["cout"])
 
-    def gn_fwd(self, x, prefix, G, want_xbar=False, sums=None):
-        """sums: per-(b,c) sum / sum of squares already produced by the conv that wrote x (Engine.conv(gn=True))."""
+    def _gn_fused_ok(self, x, G, other=None):
+        """One-launch GroupNorm (gn_fused_small.cu) when the tensors of the pass fit the L2 (second sweep = L2 hits)."""
+        nbytes = x.numel() * x.element_size() + (0 if other is None else other.numel() * other.element_size())
+        if self.gn_fused_bytes <= 0 or nbytes > self.gn_fused_bytes:
+            return False
         B, N, C = ops._bnc(x)
-        if sums is None:
-            sums = self.fwd_arena.take(B, C, 2)
-            ops.chan_stats(x, sums)
+        return ops.gn_fused_supported(B, N, C, G)
+
+    def gn_apply_fwd(self, x, y, prefix, G, post=None, act=ops.ACT_NONE, want_xbar=False, sums=None):
+        """GroupNorm forward: y = act(GN(x)) * post (y None: statistics / affine only, the consumer applies it).
+        sums: per-(b,c) sum / sum of squares already produced by the conv that wrote x (Engine.conv(gn=True)).
+        -> (ab [B][C][2], mean_rstd [B][G][2], xbar [B][C] or None), all needed again by the backward pass."""
+        B, N, C = ops._bnc(x)
+        gamma, beta = self.P[prefix + ".weight"].detach(), self.P[prefix + ".bias"].detach()
         ab = self._empty(B, C, 2, dtype=torch.float32)
         mr = self._empty(B, G, 2, dtype=torch.float32)
         xbar = self._empty(B, C, dtype=torch.float32) if want_xbar else None
-        ops.gn_finalize(sums, self.P[prefix + ".weight"].detach(), self.P[prefix + ".bias"].detach(), ab, mr, xbar,
-                        B, C, G, N)
+        if self._gn_fused_ok(x, G):
+            ops.gn_fused_fwd(x, y, gamma, beta, G, sums, post, act, ab, mr, xbar)
+            return ab, mr, xbar
+        if sums is None:
+            sums = self.fwd_arena.take(B, C, 2)
+            ops.chan_stats(x, sums)
+        ops.gn_finalize(sums, gamma, beta, ab, mr, xbar, B, C, G, N)
+        if y is not None:
+            ops.affine_act(x, y, ab, post, act)
         return ab, mr, xbar
 
     def gn_bwd(self, dy, x, ab, mr, prefix, G, act, post, addbc, dx, accumulate):
         B, N, C = ops._bnc(x)
+        if self._gn_fused_ok(x, G, dy):
+            ops.gn_fused_bwd(dy, x, ab, mr, self.P[prefix + ".weight"].detach(), G, post, addbc, act, dx, accumulate,
+                             self.pg[prefix + ".weight"], self.pg[prefix + ".bias"])
+            return
         pq = self.bwd_arena.take(B, C, 2)
         # with an activation, dz = dy * post * act'(.) is written back over dy by the reduce pass (every such dy is
         # consumed only here), so the derivative is evaluated once and the apply pass is a pure stream
@@ -467,9 +419,8 @@ class Engine:
         C = cfg.dims[s]
         y = self._empty(B, Ho, Wo, C)
         sums = self.conv(xin, name + ".proj.weight", y, bias=name + ".proj.bias", gn=True)
-        ab, mr, _ = self.gn_fwd(y, name + ".norm", C // cfg.gn_div, sums=sums)
         x0 = self._empty(B, Ho, Wo, C, dtype=torch.float32)
-        ops.affine_act(y, x0, ab, None, ops.ACT_NONE)
+        ab, mr, _ = self.gn_apply_fwd(y, x0, name + ".norm", C // cfg.gn_div, sums=sums)
         rec = dict(xin=xin, y=y, ab=ab, mr=mr) if save else None
         return x0, rec
 
@@ -483,7 +434,6 @@ class Engine:
         self.conv_wgrad(rec["xin"], dy, name + ".proj.weight", bias=name + ".proj.bias")
         if dxin is not None:
             self.conv_dgrad(dy, name + ".proj.weight", dxin, accumulate)
-        self._leaf_join()
 
     def block_fwd(self, s, i, x, dp, dp_mlp, save):
         cfg = self.cfg
@@ -494,9 +444,8 @@ class Engine:
         rC = int(C * cfg.ff[s])
         G = C // cfg.gn_div
         f32 = torch.float32
-        ab1, mr1, xbar1 = self.gn_fwd(x, p + ".norm1", G, want_xbar=True)
         x1 = self._empty(B, H, W, C)
-        ops.affine_act(x, x1, ab1, None, ops.ACT_NONE)
+        ab1, mr1, xbar1 = self.gn_apply_fwd(x, x1, p + ".norm1", G, want_xbar=True)
         q = self._empty(B, H, W, C)
         self.conv(x1, p + ".attn.q.weight", q, bias=p + ".attn.q.bias")
         rec = {}
@@ -504,9 +453,8 @@ class Engine:
             Hs, Ws = H // sr, W // sr
             xs = self._empty(B, Hs, Ws, C)
             sums_s = self.conv(x1, p + ".attn.sr.weight", xs, bias=p + ".attn.sr.bias", gn=True)
-            ab_s, mr_s, _ = self.gn_fwd(xs, p + ".attn.norm", G, sums=sums_s)
             xsn = self._empty(B, Hs, Ws, C)
-            ops.affine_act(xs, xsn, ab_s, None, ops.ACT_NONE)
+            ab_s, mr_s, _ = self.gn_apply_fwd(xs, xsn, p + ".attn.norm", G, sums=sums_s)
             kin = xsn
             rec.update(xs=xs, ab_s=ab_s, mr_s=mr_s, xsn=xsn)
         else:
@@ -525,18 +473,16 @@ class Engine:
         ops.attn_out_residual(x.view(B, N, C), pv, sc, self.P[p + ".attn.proj.bias"].detach(), dp,
                               x_mid.view(B, N, C))
         # Mix-FFN
-        ab2, mr2, _ = self.gn_fwd(x_mid, p + ".norm2", G)
         x2 = self._empty(B, H, W, C)
-        ops.affine_act(x_mid, x2, ab2, None, ops.ACT_NONE)
+        ab2, mr2, _ = self.gn_apply_fwd(x_mid, x2, p + ".norm2", G)
         h1 = self._empty(B, H, W, rC)
         sums_m1 = self.conv(x2, p + ".mlp1.fc1.weight", h1, bias=p + ".mlp1.fc1.bias", gn=True)
-        ab_m1, mr_m1, _ = self.gn_fwd(h1, p + ".mlp1.norm1", rC // cfg.gn_div, sums=sums_m1)
+        ab_m1, mr_m1, _ = self.gn_apply_fwd(h1, None, p + ".mlp1.norm1", rC // cfg.gn_div, sums=sums_m1)  # applied by the dwconv
         h2 = self._empty(B, H, W, rC)
         ops.dwconv_fwd(h1, ab_m1, self.P[p + ".mlp1.dwconv.dwconv.weight"].detach(),
                        self.P[p + ".mlp1.dwconv.dwconv.bias"].detach(), h2)
-        ab_m2, mr_m2, _ = self.gn_fwd(h2, p + ".mlp1.norm2", G)
         h3 = self._empty(B, H, W, rC)
-        ops.affine_act(h2, h3, ab_m2, None, ops.ACT_GELU)
+        ab_m2, mr_m2, _ = self.gn_apply_fwd(h2, h3, p + ".mlp1.norm2", G, act=ops.ACT_GELU)
         y2 = self._empty(B, H, W, C)
         self.conv(h3, p + ".mlp1.fc2.weight", y2, bias=p + ".mlp1.fc2.bias")
         x_out = self._empty(B, H, W, C, dtype=f32)
@@ -577,7 +523,7 @@ class Engine:
                     None, None, dh1, False)
         del dh1n
         self.conv_wgrad(rec["x2"], dh1, p + ".mlp1.fc1.weight", bias=p + ".mlp1.fc1.bias")
-        dx2 = self._empty(B, H, W, C)       # not dy2: the fc2 weight gradient may still be reading it (leaf stream)
+        dx2 = dy2   # reuse
         self.conv_dgrad(dh1, p + ".mlp1.fc1.weight", dx2, False)
         self.gn_bwd(dx2, rec["x_mid"], rec["ab2"], rec["mr2"], p + ".norm2", G, ops.ACT_NONE, None, None, dx, True)
         # ---- attention branch (dx is now the grad wrt x_mid)
@@ -603,7 +549,7 @@ class Engine:
             self.conv_wgrad(rec["xsn"], dk, p + ".attn.k.weight", bias=p + ".attn.k.bias")
             dxsn = self._empty(*kshape)
             self.conv_dgrad(dk, p + ".attn.k.weight", dxsn, False)
-            dxs = self._empty(*kshape)      # not dk: the k weight gradient may still be reading it (leaf stream)
+            dxs = dk   # reuse
             self.gn_bwd(dxsn, rec["xs"], rec["ab_s"], rec["mr_s"], p + ".attn.norm", G, ops.ACT_NONE, None, None,
                         dxs, False)
             self.conv_wgrad(rec["x1"], dxs, p + ".attn.sr.weight", bias=p + ".attn.sr.bias")
@@ -612,7 +558,6 @@ class Engine:
             self.conv_wgrad(rec["x1"], dk, p + ".attn.k.weight", bias=p + ".attn.k.bias")
             self.conv_dgrad(dk, p + ".attn.k.weight", dx1, True)
         self.gn_bwd(dx1, rec["x"], rec["ab1"], rec["mr1"], p + ".norm1", G, ops.ACT_NONE, None, dxbar, dx, True)
-        self._leaf_join()
 
     # ------------------------------------------------------------------ decoder pieces
     def convlayer_fwd(self, x, prefix, dest, post, save, act=ops.ACT_GELU):
@@ -622,8 +567,8 @@ class Engine:
         B, H, W, _ = x.shape
         y = self._empty(B, H, W, L["cout"])
         sums = self.conv(x, name, y, gn=True)
-        ab, mr, _ = self.gn_fwd(y, prefix + ".model.1", L["cout"] // self.cfg.gn_div, sums=sums)
-        ops.affine_act(y, dest, ab, post, act)
+        ab, mr, _ = self.gn_apply_fwd(y, dest, prefix + ".model.1", L["cout"] // self.cfg.gn_div, post=post, act=act,
+                                      sums=sums)
         return dict(x=x, y=y, ab=ab, mr=mr, post=post) if save else None
 
     def convlayer_bwd(self, prefix, rec, ddest, dx, accumulate):
@@ -719,6 +664,11 @@ class Engine:
                 d = ops.make_desc(a, out, a.shape[-1], row_hi[li] - row_lo[li], 3, 3, 1, 1, transposed=1,
                                   w_tap_stride=off[3], w_koff=off[li])
                 ev = self._timed("dgrad", name + ".model.0.weight")
+                if ev is not None:
+                    # this launch is the OUTPUT-channel block finished after layer li: rows row_lo..row_hi of the
+                    # concat gradient from the stacked [dy_li | .. | dy_2] (K = 9 * its width), not layer li's own dgrad
+                    self.timed_flops[("dgrad", name + ".model.0.weight")] = \
+                        2.0 * B_ * H_ * W_ * (row_hi[li] - row_lo[li]) * 9 * a.shape[-1]
                 ops.conv_fwd(d, a, wb[row_lo[li]:row_hi[li]], None, out, use_tc=True)
                 if ev is not None:
                     ev.record()
@@ -792,11 +742,6 @@ class Engine:
             self.device = x.device
             self.fwd_arena = ZeroArena(self.device)
             self.bwd_arena = ZeroArena(self.device)
-            self.leaf_stream = torch.cuda.Stream(self.device) if self.leaf_stages else None
-            nmax = max([1] + list(self.split.values()))
-            self.chunk_streams = [torch.cuda.Stream(self.device) for _ in range(nmax)] if nmax > 1 else []
-            self.chunk_leaf_streams = [torch.cuda.Stream(self.device) if self.leaf_stages else None
-                                       for _ in range(nmax)] if nmax > 1 else []
         if packed:
             (B, H, W, _), cin = x.shape, cfg.cin
         else:
@@ -836,38 +781,14 @@ class Engine:
             xr, prec = self.pe_fwd(s, cur, save)
             pe_recs.append(prec)
             brs = []
-            chunks = self._chunks(s, B)
+            for i in range(cfg.depths[s]):
+                dp, dp_mlp = (None if m is None else m.to(self.device, f32).contiguous()
+                              for m in (dps[2 * bi], dps[2 * bi + 1]))
+                xr, brec = self.block_fwd(s, i, xr, dp, dp_mlp, save)
+                brs.append(brec)
+                bi += 1
             st = self._empty(*xr.shape)
-            if len(chunks) == 1:
-                for i in range(cfg.depths[s]):
-                    dp, dp_mlp = (None if m is None else m.to(self.device, f32).contiguous()
-                                  for m in (dps[2 * bi], dps[2 * bi + 1]))
-                    xr, brec = self.block_fwd(s, i, xr, dp, dp_mlp, save)
-                    brs.append(brec)
-                    bi += 1
-                ops.scale_cast(xr, None, st)
-            else:
-                # one stream per batch chunk; launches are issued block by block, round-robin over the chunks
-                masks_s = []
-                for i in range(cfg.depths[s]):
-                    masks_s.append(tuple(None if m is None else m.to(self.device, f32).contiguous()
-                                         for m in (dps[2 * bi], dps[2 * bi + 1])))
-                    bi += 1
-                xs = [xr[b0:b1] for (b0, b1) in chunks]
-                self._fork(len(chunks))
-                for i in range(cfg.depths[s]):
-                    recs_i = []
-                    for c, (b0, b1) in enumerate(chunks):
-                        dp, dp_mlp = (None if m is None else m[b0:b1] for m in masks_s[i])
-                        with torch.cuda.stream(self.chunk_streams[c]):
-                            xs[c], brec = self.block_fwd(s, i, xs[c], dp, dp_mlp, save)
-                        recs_i.append(brec)
-                    brs.append(recs_i)
-                for c, (b0, b1) in enumerate(chunks):
-                    with torch.cuda.stream(self.chunk_streams[c]):
-                        ops.scale_cast(xs[c], None, st[b0:b1])
-                self._join(len(chunks))
-                del xs
+            ops.scale_cast(xr, None, st)
             blk_recs.append(brs)
             stage_T.append(st)
             cur = st
@@ -1058,25 +979,11 @@ class Engine:
         yield "decoder"
         # ---- encoder, last stage first
         for s in (3, 2, 1, 0):
-            self._leaf_on = s in self.leaf_stages
             dx = torch.zeros(*stage_T[s].shape, dtype=f32, device=self.device)
             ops.add_f32(dx, dstage[s])
-            chunks = self._chunks(s, B)
-            if len(chunks) == 1:
-                for i in reversed(range(cfg.depths[s])):
-                    self.block_bwd(s, i, S["blk"][s][i], dx)
-            else:
-                main_leaf = self.leaf_stream
-                self._fork(len(chunks))
-                for i in reversed(range(cfg.depths[s])):
-                    for c, (b0, b1) in enumerate(chunks):
-                        self.leaf_stream = self.chunk_leaf_streams[c]
-                        with torch.cuda.stream(self.chunk_streams[c]):
-                            self.block_bwd(s, i, S["blk"][s][i][c], dx[b0:b1])
-                self.leaf_stream = main_leaf
-                self._join(len(chunks))
+            for i in reversed(range(cfg.depths[s])):
+                self.block_bwd(s, i, S["blk"][s][i], dx)
             self.pe_bwd(s, S["pe"][s], dx, dstage[s - 1] if s > 0 else None, True)
-            self._leaf_on = False
             if s == 0:
                 grads = dict(self.pg)
                 for n in self.no_grad_names(sup_grad):

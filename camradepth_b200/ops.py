@@ -198,6 +198,23 @@ def gnact_bwd_apply(dy, x, ab, post, addbc, act, coef, dx, accumulate):
                           dcode(dx), int(accumulate), B, N, C, _ld(dy), _ld(x), _ld(dx), stream())
 
 
+def gn_fused_supported(B, N, C, G):
+    return bool(load().crd_gn_fused_supported(B, N, C, G))
+
+
+def gn_fused_fwd(x, y, gamma, beta, G, sums, post, act, ab, mean_rstd, xbar, eps=1e-5):
+    """One-launch GroupNorm forward (statistics + finalize + apply); y may be None (finalize only)."""
+    B, N, C = _bnc(x)
+    K.crd_gn_fused_fwd(P(x), dcode(x), P(y), dcode(y) if y is not None else 0, P(gamma), P(beta), P(sums), P(post), act,
+                       P(ab), P(mean_rstd), P(xbar), B, N, C, G, _ld(x), _ld(y) if y is not None else 8, eps, stream())
+
+
+def gn_fused_bwd(dy, x, ab, mean_rstd, gamma, G, post, addbc, act, dx, accumulate, dgamma, dbeta):
+    B, N, C = _bnc(x)
+    K.crd_gn_fused_bwd(P(dy), dcode(dy), P(x), dcode(x), P(ab), P(mean_rstd), P(gamma), P(post), P(addbc), act, P(dx),
+                       dcode(dx), int(accumulate), P(dgamma), P(dbeta), B, N, C, G, _ld(dy), _ld(x), _ld(dx), stream())
+
+
 # ------------------------------------------------------------------ encoder pieces
 def dwconv_fwd(x, ab, w, bias, y):
     B, H, W, C = x.shape

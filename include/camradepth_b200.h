@@ -145,6 +145,24 @@ CRD_API int crd_gnact_bwd_apply(const void* dy, int dy_dtype, const void* x, int
                         int dx_dtype, int accumulate, int B, long long N, int C, int lddy, int ldx, int lddx,
                         crd_stream_t stream);
 
+/* GroupNorm forward / backward in ONE launch each for tensors that fit the L2 (every GroupNorm of the encoder):
+ * one CTA per (sample, channel tile of whole groups) sweeps its [N][tile] slab twice -- statistics, in-CTA finalize,
+ * apply -- instead of the three launches of the protocol above.  Same arithmetic.
+ *   fwd: y = act(a*x + b) * post.  sums_in (optional): per-(b,c) sums already produced by the conv read-out
+ *        (crd_conv_fwd_tc gn_sums), then the statistics sweep is skipped.  y == NULL: finalize only.
+ *        ab_out [B][C][2], mean_rstd_out [B][G][2], xbar_out [B][C] (each optional) are written for later use.
+ *   bwd: as crd_gnact_bwd_reduce + crd_gn_bwd_finalize + crd_gnact_bwd_apply; with an activation dy is overwritten
+ *        by dz (it is consumed here).  dx may not alias dy. */
+CRD_API int crd_gn_fused_supported(int B, long long N, int C, int G);
+CRD_API int crd_gn_fused_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta,
+                     const float* sums_in, const float* post, int act, float* ab_out, float* mean_rstd_out,
+                     float* xbar_out, int B, long long N, int C, int G, int ldx, int ldy, float eps,
+                     crd_stream_t stream);
+CRD_API int crd_gn_fused_bwd(void* dy, int dy_dtype, const void* x, int x_dtype, const float* ab, const float* mean_rstd,
+                     const float* gamma, const float* post, const float* addbc, int act, void* dx, int dx_dtype,
+                     int accumulate, float* dgamma, float* dbeta, int B, long long N, int C, int G, int lddy, int ldx,
+                     int lddx, crd_stream_t stream);
+
 /* ---------------------------------------------------------------- encoder block pieces
  * DWConv (simplified_attention.py:313-323) fused with the preceding GroupNorm apply (Mlp.norm1, :36). */
 CRD_API int crd_dwconv3x3_fwd(const void* x, int dtype, const float* ab, const float* w /*[C][9]*/, const float* bias,

@@ -198,6 +198,35 @@ def test_groupnorm_protocol(shape, act, dtype):
     dx3 = torch.empty(B, H, W, C, dtype=dtype, device=d)
     ops.gnact_bwd_apply(dz, xb, ab, None, None, ops.ACT_NONE, coef, dx3, False)
     assert rel(nchw(dx3), gx_ref) < max(t, 2 * TOL[dtype])
+    # ---- the one-launch variants (gn_fused_small.cu): same results from one kernel per direction
+    assert ops.gn_fused_supported(B, N, C, G)
+    ab_f, mr_f, xbar_f = torch.empty(B, C, 2, device=d), torch.empty(B, G, 2, device=d), torch.empty(B, C, device=d)
+    yfb = torch.zeros(B, H, W, C + 8, dtype=dtype, device=d)
+    yf = yfb[..., 8:]
+    ops.gn_fused_fwd(xb, yf, gamma, beta, G, None, post, act, ab_f, mr_f, xbar_f)
+    assert rel(nchw(yf), yr) < TOL[dtype] and float(yfb[..., :8].abs().max()) == 0
+    assert rel(ab_f, ab) < 1e-5 and rel(mr_f, mr) < 1e-5 and rel(xbar_f, xbar) < 1e-5
+    # statistics handed in (conv read-out) and finalize-only form
+    ab_g, mr_g = torch.empty_like(ab), torch.empty_like(mr)
+    ops.gn_fused_fwd(xb, None, gamma, beta, G, sums, None, 0, ab_g, mr_g, None)
+    assert rel(ab_g, ab) < 1e-6 and rel(mr_g, mr) < 1e-6
+    yg = torch.empty(B, H, W, C, dtype=torch.float32, device=d)
+    ops.gn_fused_fwd(xb, yg, gamma, beta, G, sums, post, act, None, None, None)
+    assert rel(nchw(yg), yr) < (1e-5 if dtype == torch.float32 else TOL[dtype])
+    dgf, dbf = torch.zeros(C, device=d), torch.zeros(C, device=d)
+    dyf = dy.clone()
+    dxf = torch.ones(B, H, W, C, dtype=torch.float32, device=d)
+    ops.gn_fused_bwd(dyf, xb, ab, mr, gamma, G, post, addbc, act, dxf, True, dgf, dbf)
+    assert rel(nchw(dxf) - 1, gx_ref) < t
+    assert rel(dgf, gg_ref) < t and rel(dbf, gb_ref) < t
+    if act:
+        assert rel(dyf, dz) < 1e-6            # dz left in place of dy, like the reduce pass does
+    else:
+        assert torch.equal(dyf, dy)
+    dyf = dy.clone()
+    dxh = torch.empty(B, H, W, C + 16, dtype=dtype, device=d)[..., 8:8 + C]
+    ops.gn_fused_bwd(dyf, xb, ab, mr, gamma, G, post, addbc, act, dxh, False, None, None)
+    assert rel(nchw(dxh), gx_ref) < max(t, TOL[dtype])
 
 
 @pytest.mark.parametrize("dtype", DT)

@@ -56,4 +56,13 @@ for (kind, name), evs in sorted(eng.timed.items(), key=lambda kv: kv[0][1]):
     st = int(name.split(".")[1])
     px = B * (12 * 26) * 4 ** st
     fl = 2.0 * px * L["cout"] * L["cin"] * L["taps"]
-    print(f"{ms:8.3f} ms x{len(evs)}  {kind:6s} {name:52s} Cin {L['cin']:4d} Cout {L['cout']:4d}  {fl / ms / 1e9:7.0f} TF/s useful")
+    note = ""
+    if (kind, name) in eng.timed_flops:
+        # stacked-K data gradients: the timed launch computes one output-channel block of the concat gradient from
+        # the dy of SEVERAL layers; credit the MACs that launch really does (summing over the three launches of a
+        # dense block gives the same total as the three per-layer dgrads)
+        fl = eng.timed_flops[(kind, name)] * len(evs)
+        note = "  (output-channel block, stacked K)"
+    else:
+        fl *= len(evs)
+    print(f"{ms:8.3f} ms x{len(evs)}  {kind:6s} {name:52s} Cin {L['cin']:4d} Cout {L['cout']:4d}  {fl / ms / 1e9:7.0f} TF/s{note}")
