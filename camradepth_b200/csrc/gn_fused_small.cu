@@ -7,12 +7,18 @@
 // owns a (sample, channel tile of whole groups) slab [N pixels][CT channels] and sweeps it twice: sweep 1 reduces
 // (the second read of the slab is an L2 hit: these tensors fit the 126 MB L2), the statistics are finalised inside
 // the CTA (shared memory, fp64 for the mean / variance), sweep 2 applies.  Same arithmetic as the three-step path.
+// Slabs with many pixels are cut over a THREAD-BLOCK CLUSTER of up to 8 CTAs (one pixel range each): the partial
+// sums meet through distributed shared memory in rank order (no atomics: the result is bit-reproducible), every
+// CTA finalises redundantly and applies its own range -- 8x the CTAs for the 5k-token maps of stage 1.
 //   forward : y = act(a*x + b) * post,   a = gamma*rstd, b = beta - mean*a        (utils.py:223-228,
 //             simplified_attention.py:36-38,141-145,184-187); optionally the sums come from the producing conv's
 //             read-out (sums_in) and sweep 1 is skipped; ab / mean_rstd / xbar are written for the backward pass
 //   backward: dz = (dy + addbc) * post * act'(a*x+b);  dx (+)= A*dz + Bq*x + Cq;  dgamma/dbeta += ...
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "../../include/camradepth_b200.h"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -31,8 +37,25 @@ __device__ __forceinline__ float gf_act_bwd(float z, int act) {
 
 struct GfGeom {
   int B, C, G, cpg, CT, cvec, rows;
-  long long N;
+  int cs;                   // cluster size (CTAs per slab)
+  long long N, per;         // pixels per sample, pixels per CTA of a cluster
 };
+
+// totals of all CTAs of the cluster, summed in rank order (deterministic); all[] is this CTA's copy
+__device__ __forceinline__ void gf_cluster_reduce(cg::cluster_group& cluster, float* tot, float* all, int n) {
+  if (cluster.num_blocks() == 1) {
+    for (int i = threadIdx.x; i < n; i += GF_THREADS) all[i] = tot[i];
+    __syncthreads();
+    return;
+  }
+  cluster.sync();                                   // every CTA's tot[] is complete and visible
+  for (int i = threadIdx.x; i < n; i += GF_THREADS) {
+    float a = 0.f;
+    for (unsigned r = 0; r < cluster.num_blocks(); r++) a += cluster.map_shared_rank(tot, r)[i];
+    all[i] = a;
+  }
+  cluster.sync();                                   // nobody leaves (or reuses tot) while a peer still reads it
+}
 
 // per-thread partial sums -> per-channel totals in shared memory: red[0][c], red[1][c]
 __device__ __forceinline__ void gf_block_reduce(const float (&s0)[8], const float (&s1)[8], float* part /*[rows][CT][2]*/,
@@ -59,27 +82,31 @@ gn_fused_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* _
                     int act, float* __restrict__ ab_out, float* __restrict__ mr_out, float* __restrict__ xbar_out,
                     GfGeom g, int ldx, int ldy, float eps) {
   extern __shared__ float sm[];
+  cg::cluster_group cluster = cg::this_cluster();
   float* part = sm;                                   // [rows][CT][2]
-  float* tot = part + g.rows * g.CT * 2;              // [2][CT]
-  float* coef = tot + 2 * g.CT;                       // [2][CT]: a, b
+  float* tot = part + g.rows * g.CT * 2;              // [2][CT] this CTA's pixel range
+  float* all = tot + 2 * g.CT;                        // [2][CT] whole slab
+  float* coef = all + 2 * g.CT;                       // [2][CT]: a, b
   const int tx = threadIdx.x % g.cvec, ty = threadIdx.x / g.cvec;
-  const int b = blockIdx.y, c0 = blockIdx.x * g.CT, c = c0 + tx * 8;
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.y, c0 = (blockIdx.x / g.cs) * g.CT, c = c0 + tx * 8;
+  const long long pbeg = (long long)rank * g.per, pend = min(g.N, pbeg + g.per);
   const TI* xb = x + (long long)b * g.N * ldx + c;
   if (sums_in == nullptr) {
     float s0[8], s1[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) { s0[j] = 0.f; s1[j] = 0.f; }
     constexpr int U = 4;
-    for (long long p = ty; p < g.N; p += (long long)U * g.rows) {
+    for (long long p = pbeg + ty; p < pend; p += (long long)U * g.rows) {
       typename Raw8<TI>::type raw[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const long long q = p + (long long)u * g.rows;
-        raw[u] = ldg16(xb + (q < g.N ? q : p) * ldx);
+        raw[u] = ldg16(xb + (q < pend ? q : p) * ldx);
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        if (p + (long long)u * g.rows >= g.N) break;
+        if (p + (long long)u * g.rows >= pend) break;
         float v[8];
         unpack8(raw[u], v);
 #pragma unroll
@@ -87,13 +114,16 @@ gn_fused_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* _
       }
     }
     gf_block_reduce(s0, s1, part, tot, tx, ty, g.CT, g.rows);
+    gf_cluster_reduce(cluster, tot, all, 2 * g.CT);
   } else {
     for (int i = threadIdx.x; i < 2 * g.CT; i += GF_THREADS) {
       const int ch = i >> 1, q = i & 1;
-      tot[q * g.CT + ch] = sums_in[((long long)b * g.C + c0 + ch) * 2 + q];
+      all[q * g.CT + ch] = sums_in[((long long)b * g.C + c0 + ch) * 2 + q];
     }
     __syncthreads();
   }
+  tot = all;
+  const bool writer = rank == 0;                      // one CTA of the cluster publishes ab / mean_rstd / xbar
   // finalize: one thread per group of this tile
   const int gpt = g.CT / g.cpg;
   if (threadIdx.x < gpt) {
@@ -105,14 +135,14 @@ gn_fused_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* _
     if (var < 0.0) var = 0.0;
     const float rstd = (float)(1.0 / sqrt(var + (double)eps));
     const int gi = c0 / g.cpg + threadIdx.x;
-    if (mr_out) { mr_out[((long long)b * g.G + gi) * 2] = (float)mean; mr_out[((long long)b * g.G + gi) * 2 + 1] = rstd; }
+    if (mr_out && writer) { mr_out[((long long)b * g.G + gi) * 2] = (float)mean; mr_out[((long long)b * g.G + gi) * 2 + 1] = rstd; }
     for (int j = 0; j < g.cpg; j++) {
       const int ch = threadIdx.x * g.cpg + j;
       const float a = gamma[c0 + ch] * rstd;
       const float bb = beta[c0 + ch] - (float)mean * a;
       coef[ch] = a; coef[g.CT + ch] = bb;
-      if (ab_out) { ab_out[((long long)b * g.C + c0 + ch) * 2] = a; ab_out[((long long)b * g.C + c0 + ch) * 2 + 1] = bb; }
-      if (xbar_out) xbar_out[(long long)b * g.C + c0 + ch] = a * (tot[ch] / (float)g.N) + bb;
+      if (ab_out && writer) { ab_out[((long long)b * g.C + c0 + ch) * 2] = a; ab_out[((long long)b * g.C + c0 + ch) * 2 + 1] = bb; }
+      if (xbar_out && writer) xbar_out[(long long)b * g.C + c0 + ch] = a * (tot[ch] / (float)g.N) + bb;
     }
   }
   __syncthreads();
@@ -126,17 +156,17 @@ gn_fused_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* _
   }
   TO* yb = y + (long long)b * g.N * ldy + c;
   constexpr int U = 4;
-  for (long long p = ty; p < g.N; p += (long long)U * g.rows) {
+  for (long long p = pbeg + ty; p < pend; p += (long long)U * g.rows) {
     typename Raw8<TI>::type raw[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const long long q = p + (long long)u * g.rows;
-      raw[u] = ldg16(xb + (q < g.N ? q : p) * ldx);
+      raw[u] = ldg16(xb + (q < pend ? q : p) * ldx);
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const long long q = p + (long long)u * g.rows;
-      if (q >= g.N) break;
+      if (q >= pend) break;
       float v[8];
       unpack8(raw[u], v);
       if (act == CRD_ACT_GELU) {
@@ -152,17 +182,21 @@ gn_fused_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* _
 }
 
 template <typename TD, typename TX, typename TO>
-__global__ void __launch_bounds__(GF_THREADS)
+__global__ void __launch_bounds__(GF_THREADS, 2)
 gn_fused_bwd_kernel(TD* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ ab,
                     const float* __restrict__ mean_rstd, const float* __restrict__ gamma, const float* __restrict__ post,
                     const float* __restrict__ addbc, int act, TO* __restrict__ dx, int accumulate, float* dgamma,
                     float* dbeta, GfGeom g, int lddy, int ldx, int lddx) {
   extern __shared__ float sm[];
+  cg::cluster_group cluster = cg::this_cluster();
   float* part = sm;
-  float* tot = part + g.rows * g.CT * 2;              // [2][CT]: sum dz, sum dz*x
-  float* coef = tot + 2 * g.CT;                       // [3][CT]: A, Bq, Cq
+  float* tot = part + g.rows * g.CT * 2;              // [2][CT]: sum dz, sum dz*x over this CTA's pixel range
+  float* all = tot + 2 * g.CT;                        // [2][CT]: over the whole slab
+  float* coef = all + 2 * g.CT;                       // [3][CT]: A, Bq, Cq
   const int tx = threadIdx.x % g.cvec, ty = threadIdx.x / g.cvec;
-  const int b = blockIdx.y, c0 = blockIdx.x * g.CT, c = c0 + tx * 8;
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.y, c0 = (blockIdx.x / g.cs) * g.CT, c = c0 + tx * 8;
+  const long long pbeg = (long long)rank * g.per, pend = min(g.N, pbeg + g.per);
   float a[8], sh[8], k1[8], k0[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) {
@@ -178,21 +212,21 @@ gn_fused_bwd_kernel(TD* __restrict__ dy, const TX* __restrict__ x, const float* 
   float s0[8], s1[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) { s0[j] = 0.f; s1[j] = 0.f; }
-  constexpr int U = 4;
-  for (long long p = ty; p < g.N; p += (long long)U * g.rows) {
+  constexpr int U = 2;                     // (two CTAs of 128 registers per SM; four loads per array in flight spilled)
+  for (long long p = pbeg + ty; p < pend; p += (long long)U * g.rows) {
     typename Raw8<TD>::type rg[U];
     typename Raw8<TX>::type rx[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const long long q = p + (long long)u * g.rows;
-      const long long qq = q < g.N ? q : p;
+      const long long qq = q < pend ? q : p;
       rg[u] = ldg16(dyb + qq * lddy);
       rx[u] = ldg16(xb + qq * ldx);
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const long long q = p + (long long)u * g.rows;
-      if (q >= g.N) break;
+      if (q >= pend) break;
       float gd[8], v[8];
       unpack8(rg[u], gd);
       unpack8(rx[u], v);
@@ -209,6 +243,9 @@ gn_fused_bwd_kernel(TD* __restrict__ dy, const TX* __restrict__ x, const float* 
     }
   }
   gf_block_reduce(s0, s1, part, tot, tx, ty, g.CT, g.rows);
+  gf_cluster_reduce(cluster, tot, all, 2 * g.CT);
+  tot = all;
+  const bool writer = rank == 0;
   const int gpt = g.CT / g.cpg;
   if (threadIdx.x < gpt) {
     const int gi = c0 / g.cpg + threadIdx.x;
@@ -227,8 +264,8 @@ gn_fused_bwd_kernel(TD* __restrict__ dy, const TX* __restrict__ x, const float* 
       coef[ch] = r * gamma[c0 + ch];
       coef[g.CT + ch] = -r * r * m2;
       coef[2 * g.CT + ch] = -r * m1 + r * r * m2 * mu;
-      if (dgamma) atomicAdd(dgamma + c0 + ch, r * (tot[g.CT + ch] - mu * tot[ch]));
-      if (dbeta) atomicAdd(dbeta + c0 + ch, tot[ch]);
+      if (dgamma && writer) atomicAdd(dgamma + c0 + ch, r * (tot[g.CT + ch] - mu * tot[ch]));
+      if (dbeta && writer) atomicAdd(dbeta + c0 + ch, tot[ch]);
     }
   }
   __syncthreads();
@@ -241,14 +278,14 @@ gn_fused_bwd_kernel(TD* __restrict__ dy, const TX* __restrict__ x, const float* 
   }
   if (inplace) __threadfence_block();                 // this thread re-reads only what it wrote itself
   TO* dxb = dx + (long long)b * g.N * lddx + c;
-  for (long long p = ty; p < g.N; p += (long long)U * g.rows) {
+  for (long long p = pbeg + ty; p < pend; p += (long long)U * g.rows) {
     typename Raw8<TD>::type rg[U];
     typename Raw8<TX>::type rx[U];
     typename Raw8<TO>::type ro[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const long long q = p + (long long)u * g.rows;
-      const long long qq = q < g.N ? q : p;
+      const long long qq = q < pend ? q : p;
       rg[u] = ldg16(dyb + qq * lddy);
       rx[u] = ldg16(xb + qq * ldx);
       if (accumulate) ro[u] = ldg16(dxb + qq * lddx);
@@ -256,7 +293,7 @@ gn_fused_bwd_kernel(TD* __restrict__ dy, const TX* __restrict__ x, const float* 
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const long long q = p + (long long)u * g.rows;
-      if (q >= g.N) break;
+      if (q >= pend) break;
       float gd[8], v[8], o[8];
       unpack8(rg[u], gd);
       unpack8(rx[u], v);
@@ -281,9 +318,33 @@ inline bool gf_geom(int B, long long N, int C, int G, GfGeom& g) {
   while (CT < 32 && C % (CT * 2) == 0) CT *= 2;
   if (CT / 8 > GF_THREADS) return false;
   g.B = B; g.C = C; g.G = G; g.cpg = cpg; g.CT = CT; g.cvec = CT / 8; g.rows = GF_THREADS / g.cvec; g.N = N;
-  return GF_THREADS % g.cvec == 0;
+  if (GF_THREADS % g.cvec) return false;
+  // cluster size: enough CTAs for ~3 per SM, every CTA keeping at least 2 unrolled trips of its thread rows
+  const long long slabs = (long long)B * (C / CT);
+  int cs = 1;
+  while (cs < 8 && slabs * cs < 3 * 148 && N / (cs * 2) >= (long long)g.rows * 8) cs *= 2;
+  g.cs = cs;
+  g.per = (N + cs - 1) / cs;
+  return true;
 }
-inline size_t gf_smem(const GfGeom& g, int ncoef) { return (size_t)(g.rows * g.CT * 2 + 2 * g.CT + ncoef * g.CT) * sizeof(float); }
+inline size_t gf_smem(const GfGeom& g, int ncoef) { return (size_t)(g.rows * g.CT * 2 + 4 * g.CT + ncoef * g.CT) * sizeof(float); }
+
+template <typename K, typename... Args>
+inline cudaError_t gf_launch(K kernel, const GfGeom& g, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((g.C / g.CT) * g.cs), (unsigned)g.B, 1);
+  cfg.blockDim = dim3(GF_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)g.cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 }  // namespace
 
@@ -301,12 +362,13 @@ extern "C" int crd_gn_fused_fwd(const void* x, int x_dtype, void* y, int y_dtype
   CRD_REQUIRE(ldx % 8 == 0 && (y == nullptr || ldy % 8 == 0) && gamma && beta);
   CRD_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0);
   if ((long long)B * N == 0) return 0;
-  const dim3 grid(C / g.CT, B);
   const size_t smem = gf_smem(g, 2);
   cudaStream_t s = (cudaStream_t)stream;
-  CRD_DISPATCH_1(x_dtype, TI, CRD_DISPATCH_1(y_dtype, TO, gn_fused_fwd_kernel<TI, TO><<<grid, GF_THREADS, smem, s>>>(
-                                  (const TI*)x, (TO*)y, gamma, beta, sums_in, post, act, ab_out, mean_rstd_out, xbar_out,
-                                  g, ldx, ldy, eps)));
+  cudaError_t err = cudaSuccess;
+  CRD_DISPATCH_1(x_dtype, TI, CRD_DISPATCH_1(y_dtype, TO, err = gf_launch(
+                                  gn_fused_fwd_kernel<TI, TO>, g, smem, s, (const TI*)x, (TO*)y, gamma, beta, sums_in, post,
+                                  act, ab_out, mean_rstd_out, xbar_out, g, ldx, ldy, eps)));
+  if (err != cudaSuccess) return (int)err;
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -320,13 +382,13 @@ extern "C" int crd_gn_fused_bwd(void* dy, int dy_dtype, const void* x, int x_dty
   CRD_REQUIRE(lddy % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0 && ab && mean_rstd && gamma && dx);
   CRD_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0);
   if ((long long)B * N == 0) return 0;
-  const dim3 grid(C / g.CT, B);
   const size_t smem = gf_smem(g, 3);
   cudaStream_t s = (cudaStream_t)stream;
-  CRD_DISPATCH_1(dy_dtype, TD, CRD_DISPATCH_1(x_dtype, TX, CRD_DISPATCH_1(dx_dtype, TO,
-      gn_fused_bwd_kernel<TD, TX, TO><<<grid, GF_THREADS, smem, s>>>((TD*)dy, (const TX*)x, ab, mean_rstd, gamma, post, addbc,
-                                                                    act, (TO*)dx, accumulate, dgamma, dbeta, g, lddy, ldx,
-                                                                    lddx))));
+  cudaError_t err = cudaSuccess;
+  CRD_DISPATCH_1(dy_dtype, TD, CRD_DISPATCH_1(x_dtype, TX, CRD_DISPATCH_1(dx_dtype, TO, err = gf_launch(
+      gn_fused_bwd_kernel<TD, TX, TO>, g, smem, s, (TD*)dy, (const TX*)x, ab, mean_rstd, gamma, post, addbc, act, (TO*)dx,
+      accumulate, dgamma, dbeta, g, lddy, ldx, lddx))));
+  if (err != cudaSuccess) return (int)err;
   CRD_LAUNCH_CHECK();
   return 0;
 }

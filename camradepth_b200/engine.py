@@ -73,7 +73,7 @@ class ZeroArena:
 
 
 class Engine:
-    def __init__(self, model, cfg, precision="bf16"):
+    def __init__(self, model, cfg, precision="bf16", deterministic=False):
         self.model = model
         self.cfg = cfg
         self.precision = precision
@@ -92,6 +92,14 @@ class Engine:
         # GroupNorm passes whose tensors total at most this many bytes run as ONE launch (two sweeps of an
         # L2-resident slab per CTA) instead of statistics / finalize / apply launches; 0 disables
         self.gn_fused_bytes = int(float(os.environ.get("CAMRADEPTH_GN_FUSED_MB", "64")) * (1 << 20))
+        # Deterministic forward: every GroupNorm statistic comes from the one-launch kernel, whose reduction order is
+        # fixed (per-thread strides, shared-memory tree, no atomics), at any tensor size; the conv read-out sums
+        # (fp32 atomics across CTAs) are not used.  The forward pass is then bit-reproducible run to run and
+        # independent of the batch a sample sits in.  (Parameter gradients still meet in fp32 atomics.)
+        self.deterministic = bool(deterministic) or os.environ.get("CAMRADEPTH_DETERMINISTIC", "0") == "1"
+        if self.deterministic:
+            self.fuse_gn_stats = False
+            self.gn_fused_bytes = 1 << 62
         self._build_layers()
         self.fwd_arena = None
         self.bwd_arena = None

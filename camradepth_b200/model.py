@@ -91,6 +91,9 @@ class CamRaDepth(nn.Module):
         # "bf16" (training path, tensor cores) or "fp32" (exact-parity mode on CUDA cores)
         self.precision = kwargs.get("precision", os.environ.get("CAMRADEPTH_PRECISION", "bf16"))
         assert self.precision in ("bf16", "fp32")
+        # bit-reproducible forward (fixed-order GroupNorm reductions instead of fp32 atomics); slower on the large
+        # decoder tensors, meant for debugging / regression runs
+        self.deterministic = bool(kwargs.get("deterministic", os.environ.get("CAMRADEPTH_DETERMINISTIC", "0") == "1"))
 
         spec = param_spec(self.cfg)
         for name, (shape, kind) in spec.items():
@@ -120,7 +123,7 @@ class CamRaDepth(nn.Module):
         key = self.precision
         eng = self._engines.get(key)
         if eng is None:
-            eng = Engine(self, self.cfg, precision=key)
+            eng = Engine(self, self.cfg, precision=key, deterministic=self.deterministic)
             self._engines[key] = eng
         else:
             eng.P = dict(self.named_parameters())

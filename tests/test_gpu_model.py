@@ -194,6 +194,36 @@ def test_properties_full_batch():
         m(torch.zeros(1, 7, 192, 400, device="cuda"))          # reference also fails on 400-wide input (F2)
 
 
+def test_deterministic_forward_mode():
+    """deterministic=True: GroupNorm statistics from fixed-order reductions (no atomics) -> the forward pass is
+    bit-identical run to run, and a sample's result does not depend on its batch mates (bitwise)."""
+    import camradepth_b200 as C
+    from camradepth_b200.synthetic import make_batch
+    C.set_model("sup_unsup_seg")
+    try:
+        torch.manual_seed(0)
+        m = C.CamRaDepth(precision="bf16", deterministic=True).cuda().eval()
+        x = make_batch(3, 192, 416, seed=2)["image"].cuda()
+        with torch.no_grad():
+            a = m(x)
+            b = m(x)
+            one = m(x[1:2])
+        for k in ("final_depth",):
+            assert torch.equal(a["depth"][k], b["depth"][k])
+            assert torch.equal(a["depth"][k][1:2], one["depth"][k])
+        assert torch.equal(a["seg"]["final_seg"], b["seg"]["final_seg"])
+        assert torch.equal(a["seg"]["unsup_map"], b["seg"]["unsup_map"])
+        assert torch.equal(a["depth"]["intermediate_depths"][3][1:2], one["depth"]["intermediate_depths"][3])
+        # and it is the same function as the default mode up to rounding noise
+        m2 = C.CamRaDepth(precision="bf16").cuda().eval()
+        m2.load_state_dict(m.state_dict())
+        with torch.no_grad():
+            c = m2(x)
+        assert relerr(c["depth"]["final_depth"], a["depth"]["final_depth"]) < 2.5e-2     # argmax-fed heads, see golden_util
+    finally:
+        C.set_model("base")
+
+
 def test_edge_cases_native_resolution_and_empty_mask():
     """Reference-native 416x800 input (args.py:19), odd batch, and the loss on an empty valid mask (NaN, like the
     reference's mean over an empty selection, loss_funcs.py:83-91)."""

@@ -220,7 +220,7 @@ def test_groupnorm_protocol(shape, act, dtype):
     assert rel(nchw(dxf) - 1, gx_ref) < t
     assert rel(dgf, gg_ref) < t and rel(dbf, gb_ref) < t
     if act:
-        assert rel(dyf, dz) < 1e-6            # dz left in place of dy, like the reduce pass does
+        assert rel(dyf, dz) < 1e-3            # dz left in place of dy, like the reduce pass does (bf16 rounding of dz)
     else:
         assert torch.equal(dyf, dy)
     dyf = dy.clone()
