@@ -91,7 +91,11 @@ class Engine:
         self.fuse_gn_stats = self.use_tc and os.environ.get("CAMRADEPTH_GN_EPILOGUE", "1") == "1"
         # GroupNorm passes whose tensors total at most this many bytes run as ONE launch (two sweeps of an
         # L2-resident slab per CTA) instead of statistics / finalize / apply launches; 0 disables
-        self.gn_fused_bytes = int(float(os.environ.get("CAMRADEPTH_GN_FUSED_MB", "64")) * (1 << 20))
+        self.gn_fused_bytes = int(float(os.environ.get("CAMRADEPTH_GN_FUSED_MB", "16")) * (1 << 20))
+        # 1x1 GEMMs with wide outputs (Mix-FFN fc1: 512 .. 1024 channels) are bound by their accumulator read-out;
+        # the GroupNorm reduction in that read-out costs more (+33 us at stage 2) than a separate statistics pass
+        # over the bf16 output (~20 us), so it is fused only up to this many output channels
+        self.gn_epilogue_max_cout = int(os.environ.get("CAMRADEPTH_GN_EPILOGUE_MAXN", "256"))
         # Deterministic forward: every GroupNorm statistic comes from the one-launch kernel, whose reduction order is
         # fixed (per-thread strides, shared-memory tree, no atomics), at any tensor size; the conv read-out sums
         # (fp32 atomics across CTAs) are not used.  The forward pass is then bit-reproducible run to run and
@@ -278,7 +282,8 @@ class Engine:
         otherwise None is returned and the caller runs the separate statistics pass."""
         L = self.L[name]
         w = self.wpack(name, 0)
-        fuse_gn = gn and self.fuse_gn_stats and act == 0 and not accumulate
+        fuse_gn = gn and self.fuse_gn_stats and act == 0 and not accumulate and \
+            (L["k"] > 1 or L["cout"] <= self.gn_epilogue_max_cout)
         if self._gemm_route(L, x) and not out_nchw:
             col = self._im2col(L, x, y.shape[1], y.shape[2])
             d = ops.make_desc(col, y, col.shape[-1], L["cout"], 1, 1, 1, 0, 0, act, accumulate, 0)
