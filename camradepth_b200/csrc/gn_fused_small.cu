@@ -319,10 +319,10 @@ inline bool gf_geom(int B, long long N, int C, int G, GfGeom& g) {
   if (CT / 8 > GF_THREADS) return false;
   g.B = B; g.C = C; g.G = G; g.cpg = cpg; g.CT = CT; g.cvec = CT / 8; g.rows = GF_THREADS / g.cvec; g.N = N;
   if (GF_THREADS % g.cvec) return false;
-  // cluster size: enough CTAs for ~3 per SM, every CTA keeping at least 2 unrolled trips of its thread rows
-  const long long slabs = (long long)B * (C / CT);
+  // cluster size: a function of the slab geometry ONLY (not of the batch size), so that a sample's statistics are
+  // reduced in the same order whatever batch it sits in; every CTA keeps >= 16 pixels per thread row
   int cs = 1;
-  while (cs < 8 && slabs * cs < 3 * 148 && N / (cs * 2) >= (long long)g.rows * 8) cs *= 2;
+  while (cs < 8 && N / (cs * 2) >= (long long)g.rows * 16) cs *= 2;
   g.cs = cs;
   g.per = (N + cs - 1) / cs;
   return true;

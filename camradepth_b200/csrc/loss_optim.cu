@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(256) mt_sumsq_kernel(const crd_opt_tensor* __r
   float s = 0.f;
   for (long long i = ck.start + threadIdx.x; i < end; i += blockDim.x) { const float g = t.g[i]; s = fmaf(g, g, s); }
   s = block_sum(s, sh);
-  if (threadIdx.x == 0) atomicAdd(sumsq + ck.tensor, s);
+  // one partial per chunk, no atomics: the per-tensor total is formed in chunk order by the update kernel, so the
+  // step is a deterministic function of the gradients and data-parallel replicas stay bit-identical
+  if (threadIdx.x == 0) sumsq[blockIdx.x] = s;
 }
 
 __global__ void __launch_bounds__(256) diffgradnorm_kernel(const crd_opt_tensor* __restrict__ table,
@@ -156,7 +158,18 @@ __global__ void __launch_bounds__(256) diffgradnorm_kernel(const crd_opt_tensor*
   long long end = ck.start + CRD_OPT_CHUNK;
   if (end > t.numel) end = t.numel;
   // Gradient-norm correction (diffGradNorm.py:82-88); the branch is evaluated on the device.
-  const float gn = sqrtf(sumsq[ck.tensor]);
+  // ||g||^2 of the tensor = its chunk partials (consecutive in the chunk list) summed in order
+  __shared__ float tot_sh;
+  if (threadIdx.x == 0) {
+    const int idx = (int)(ck.start / CRD_OPT_CHUNK);
+    const int cnt = (int)((t.numel + CRD_OPT_CHUNK - 1) / CRD_OPT_CHUNK);
+    const float* pp = sumsq + ((long long)blockIdx.x - idx);
+    float a = 0.f;
+    for (int k = 0; k < cnt; k++) a += pp[k];
+    tot_sh = a;
+  }
+  __syncthreads();
+  const float gn = sqrtf(tot_sh);
   const float egn = 0.95f * egn_in[ck.tensor] + 0.05f * gn;
   const float corr = (egn > gn) ? egn / (gn + 1e-8f) : 1.f;
   if (ck.start == 0 && threadIdx.x == 0) egn_out[ck.tensor] = egn;

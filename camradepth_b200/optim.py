@@ -118,11 +118,10 @@ class diffGradNorm(Optimizer):
                     egn = torch.stack([self.state[p]['exp_grad_norm'].reshape(()) for p in plist]).contiguous()
                     pp = torch.stack([egn, torch.zeros_like(egn)]).contiguous()
                     ent = [key, torch.from_numpy(table).to(dev), torch.from_numpy(ck).to(dev), ck.shape[0], pp, 0,
-                           torch.zeros(T, dtype=torch.float32, device=dev),
+                           torch.zeros(ck.shape[0], dtype=torch.float32, device=dev),     # per-chunk partials
                            torch.zeros(1, dtype=torch.float32, device=dev)]
                     self._tables[gi] = ent
                 _, table_d, ck_d, nchunks, pp, cur, sumsq, hyper = ent
-                sumsq.zero_()
                 egn_in, egn_out = pp[cur], pp[1 - cur]
                 ops.mt_sumsq(table_d, ck_d, nchunks, sumsq)
                 if not torch.cuda.is_current_stream_capturing():

@@ -286,6 +286,8 @@ typedef struct {
 } crd_opt_tensor;
 typedef struct { int tensor; int pad; long long start; } crd_opt_chunk;   /* chunk of CRD_OPT_CHUNK elements */
 #define CRD_OPT_CHUNK 16384
+/* sumsq: nchunks floats, one partial sum of squares per chunk (no atomics; crd_diffgradnorm_update adds the partials
+ * of a tensor in chunk order, so the update is deterministic and data-parallel replicas stay bit-identical) */
 CRD_API int crd_mt_sumsq(const crd_opt_tensor* table, const crd_opt_chunk* chunks, int nchunks, float* sumsq,
                  crd_stream_t stream);
 /* step_size[0] (DEVICE scalar, so a CUDA-graph replay sees fresh values) = lr*sqrt(1-beta2^t)/((1-beta1^t)+1e-8)

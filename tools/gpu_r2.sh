@@ -34,7 +34,7 @@ ab)     # A/B of engine switches: AB="CAMRADEPTH_SPLIT=;CAMRADEPTH_LEAF_STAGES="
           echo "== ${kv:-default}" >> gpurun_out/${TAG}_ab.txt
           env ${kv} timeout 600 python bench.py --quick --steps 10 --warmup 3 >> gpurun_out/${TAG}_ab.txt 2>/dev/null
         done; cat gpurun_out/${TAG}_ab.txt ;;
-det)    timeout 300 python tools/det_check.py base > gpurun_out/${TAG}_det_check.txt 2>&1; tail -20 gpurun_out/${TAG}_det_check.txt ;;
+det)    timeout 300 python tools/det_check.py ${DET_VARIANT:-base} > gpurun_out/${TAG}_det_check.txt 2>&1; tail -20 gpurun_out/${TAG}_det_check.txt ;;
 dp2)    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_check.py supervised_seg fp32 > gpurun_out/${TAG}_dp_check.txt 2>&1; tail -4 gpurun_out/${TAG}_dp_check.txt
         timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/dp_check.py base bf16 >> gpurun_out/${TAG}_dp_check.txt 2>&1; tail -3 gpurun_out/${TAG}_dp_check.txt ;;
 benchN) N=${NGPU:-2}; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N > gpurun_out/${TAG}_bench_${N}gpu.json 2> gpurun_out/${TAG}_bench_${N}gpu.err; tail -c 1500 gpurun_out/${TAG}_bench_${N}gpu.json; tail -5 gpurun_out/${TAG}_bench_${N}gpu.err ;;
