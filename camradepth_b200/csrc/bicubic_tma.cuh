@@ -249,7 +249,7 @@ inline bool bc_tma_enabled() {
 inline bool bc_tma_eligible(int dtype, int B, int H, int W, int C, const void* in, int ld_in, const void* out,
                             int ld_out) {
   if (!bc_tma_enabled() || dtype != CRD_BF16 || C % 8 || C > DW_CH * BC_MAX_TILES) return false;
-  if (H < 3 || W < 4 || (long long)B * H * W * C < (1LL << 18)) return false;
+  if (H < 3 || W < 4 || B < 1 || (long long)H * W * C < (1LL << 13)) return false;      // per sample, see dwconv_tma.cuh
   if (((uintptr_t)in & 15) || ld_in % 8 || ((uintptr_t)out & 7) || ld_out % 4) return false;
   return true;
 }

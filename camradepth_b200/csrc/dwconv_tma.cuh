@@ -240,7 +240,9 @@ inline bool dw_tma_enabled() {
 }
 inline bool dw_tma_eligible(int dtype, int B, int H, int W, int C, const void* p0, const void* p1, const void* p2) {
   if (!dw_tma_enabled() || dtype != CRD_BF16 || C % DW_CH) return false;
-  if (H < 2 || W < 4 || (long long)B * H * W * C < (1LL << 19)) return false;
+  // size rule per SAMPLE (= the old per-tensor rule at batch 32): the kernel choice, hence the arithmetic order, must
+  // not depend on the batch a sample sits in (deterministic mode asserts bitwise batch independence)
+  if (H < 2 || W < 4 || B < 1 || (long long)H * W * C < (1LL << 14)) return false;
   if (((uintptr_t)p0 & 15) || ((uintptr_t)p1 & 15) || ((uintptr_t)p2 & 7)) return false;
   return true;
 }

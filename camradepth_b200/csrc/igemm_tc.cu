@@ -42,6 +42,13 @@ struct TcParams {
   int nstages, stage_bytes; // smem ring geometry: stage = A (16 KB) + B (bn * 128 B)
   int tmem_cols;            // 128 or 256
   int ldy, out_f32, act, accumulate;
+  // Strided convolutions as implicit GEMM (simplified_attention.py:68,158-160): the activation operand comes through
+  // a 5-D tensor map that splits H and W into (position / stride, position % stride), so every tap of a strided
+  // window is a plain TMA box -- no im2col buffer.
+  //   smode 1 (k == stride, pad 0: spatial-reduction convs): dims {c, w%s, w/s, h%s, b*(H/s) + h/s}, tap = coords
+  //   smode 2 (k 3, stride 2, pad 1: patch embeddings 2-4, Cin % 64 == 0): dims {(w%s)*Cin + c, w/s, h%s, h/s, b}
+  int smode, cstride;
+  int gn_rows;              // smode 1: output rows per sample (tiles run over the merged (b, oh) axis)
   int pipe;                 // 1x1 GEMMs: software-pipelined accumulator read-out (CAMRADEPTH_TC_PIPE, default on)
   int gnN;                  // pixels per sample (flat mode: sample of a pixel = pix / gnN) for the GroupNorm sums
   // fused conv + argmax (Seg_Block, utils.py:95-100): am_ncls > 0 -> nothing is written to y; the per-pixel
@@ -358,6 +365,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_expect_tx(bar_full + 8 * s, tx);
         if (p.flat) {
           tma_load_2d(sa, &map_a, bar_full + 8 * s, c0, (int)m0);
+        } else if (p.smode == 1) {
+          const int kh = tap / p.KW, kw = tap - kh * p.KW;
+          tma_load_5d(sa, &map_a, bar_full + 8 * s, c0, kw, ow0, kh, oh0);
+        } else if (p.smode == 2) {
+          const int kh = tap / p.KW, kw = tap - kh * p.KW;
+          // tap offset t = k - pad in input pixels -> (t div s, t mod s) with floor division (t = -1 -> (-1, s-1))
+          const int th_ = kh - p.pad, tw_ = kw - p.pad;
+          const int dh = th_ >= 0 ? th_ / p.cstride : -((-th_ + p.cstride - 1) / p.cstride);
+          const int dw = tw_ >= 0 ? tw_ / p.cstride : -((-tw_ + p.cstride - 1) / p.cstride);
+          const int ph_ = th_ - dh * p.cstride, pw_ = tw_ - dw * p.cstride;
+          tma_load_5d(sa, &map_a, bar_full + 8 * s, pw_ * p.Cin + c0, ow0 + dw, ph_, oh0 + dh, b);
         } else {
           const int kh = tap / p.KW, kw = tap - kh * p.KW;
           const int dh = p.transposed ? (p.pad - kh) : (kh - p.pad);
@@ -405,6 +423,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int oh = oh0 + ty, ow = ow0 + tx;
       ok = oh < p.Ho && ow < p.Wo;
       pix = ((long long)b * p.Ho + oh) * p.Wo + ow;
+      if (p.smode == 1 && gn) sb = oh / p.gn_rows;
     }
     if (p.am_ncls) epilogue_argmax(p, tmem_base + ((uint32_t)(lg * 32) << 16), ok, pix, bias);
     else epilogue_rows(p, tmem_base + ((uint32_t)(lg * 32) << 16), n0, ok, pix, bias, yv, gn, sb, p.pipe != 0);
@@ -741,18 +760,30 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
   // fused GroupNorm statistics: sums of the fp32 results (after the bias), so no activation / accumulation
   CRD_REQUIRE(gn_sums == nullptr || (d->act == CRD_ACT_NONE && !d->accumulate));
   CRD_REQUIRE(d->in_dtype == CRD_BF16 && (d->out_dtype == CRD_BF16 || d->out_dtype == CRD_F32));
-  CRD_REQUIRE(d->stride == 1 && !d->out_nchw && d->Ho == d->H && d->Wo == d->W);
+  CRD_REQUIRE(d->stride >= 1 && !d->out_nchw);
   CRD_REQUIRE(d->Cin % 8 == 0 && d->ldx % 8 == 0 && d->ldy % 8 == 0);
   CRD_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)y & 15) == 0);
-  CRD_REQUIRE(d->KH == d->KW && 2 * d->pad == d->KH - 1);
+  CRD_REQUIRE(d->KH == d->KW);
+  int smode = 0;
+  if (d->stride > 1) {
+    const int cs = d->stride;
+    CRD_REQUIRE(!d->transposed && !am && d->H % cs == 0 && d->W % cs == 0 && d->ldx == d->Cin);
+    CRD_REQUIRE(d->Ho == d->H / cs && d->Wo == d->W / cs);
+    if (d->KH == cs && d->pad == 0) smode = 1;
+    else if (d->KH == 3 && cs == 2 && d->pad == 1 && d->Cin % 64 == 0) smode = 2;
+    else return -1998;                                   // other strided shapes: the caller's im2col route
+  } else {
+    CRD_REQUIRE(d->Ho == d->H && d->Wo == d->W && 2 * d->pad == d->KH - 1);
+  }
   const long long P = (long long)d->B * d->H * d->W;
   if (P == 0) return 0;
   static unsigned long long attr_v1 = 0;
   if (int e = ensure_smem_attr(conv_tc_kernel, TC_SMEM_BUDGET + 2048, attr_v1)) return e;
   TcParams p;
-  p.flat = (d->KH == 1);
+  p.flat = (d->KH == 1 && d->stride == 1);
+  p.smode = smode; p.cstride = d->stride; p.gn_rows = d->Ho;
   p.KH = d->KH; p.KW = d->KW; p.pad = d->pad; p.transposed = d->transposed;
-  p.Ho = d->Ho; p.Wo = d->Wo; p.P = P;
+  p.Ho = smode == 1 ? d->B * d->Ho : d->Ho; p.Wo = d->Wo; p.P = P;
   p.Cin = d->Cin; p.Cout = d->Cout;
   p.wstride = d->w_tap_stride ? d->w_tap_stride : d->Cin;
   p.woff = d->w_koff;
@@ -760,22 +791,38 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
   p.ldy = d->ldy; p.out_f32 = d->out_dtype == CRD_F32; p.act = d->act; p.accumulate = d->accumulate;
   p.gnN = d->H * d->W;
   {
+    // pipelined read-out: measured faster only when the read-out also carries the GroupNorm reduction
+    // (fc1-type: 77.9 -> 70.4 us) and slightly slower for plain wide outputs (35.7 -> 37.5 us)
     static int pipe_env = -1;
     if (pipe_env < 0) { const char* e = getenv("CAMRADEPTH_TC_PIPE"); pipe_env = (e && e[0] == '0') ? 0 : 1; }
-    p.pipe = (pipe_env && p.flat) ? 1 : 0;
+    p.pipe = (pipe_env && p.flat && gn_sums != nullptr) ? 1 : 0;
   }
   p.am_ncls = am ? am->ncls : 0;
   p.am0 = am ? (bf16*)am->m0 : nullptr; p.am_ld0 = am ? am->ld0 : 0;
   p.am1 = am ? (bf16*)am->m1 : nullptr; p.am_ld1 = am ? am->ld1 : 0;
   p.amf = am ? am->mf : nullptr;
-  // spatial patch: 16 wide unless the image is narrower
-  p.TW = d->W >= 16 ? 16 : (d->W >= 8 ? 8 : 4);
+  // spatial patch over the OUTPUT image: 16 wide unless the image is narrower (smode 1: one image of B*Ho rows)
+  const int Wt = smode ? d->Wo : d->W, Ht = smode == 1 ? d->B * d->Ho : (smode == 2 ? d->Ho : d->H);
+  const int Bt = smode == 1 ? 1 : d->B;
+  p.TW = Wt >= 16 ? 16 : (Wt >= 8 ? 8 : 4);
   p.TH = TC_BM / p.TW;
-  p.tiles_w = (d->W + p.TW - 1) / p.TW;
-  p.tiles_h = (d->H + p.TH - 1) / p.TH;
+  p.tiles_w = (Wt + p.TW - 1) / p.TW;
+  p.tiles_h = (Ht + p.TH - 1) / p.TH;
   CUtensorMap map_a, map_b;
   int rc;
-  if (p.flat) {
+  if (smode == 1) {
+    const cuuint64_t cs = d->stride, C2 = (cuuint64_t)d->Cin * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)d->Cin, cs, (cuuint64_t)d->W / cs, cs, (cuuint64_t)d->B * (d->H / cs)};
+    cuuint64_t str[4] = {C2, cs * C2, (cuuint64_t)d->W * C2, cs * d->W * C2};
+    cuuint32_t box[5] = {TC_BK, 1, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH};
+    rc = make_map(&map_a, x, 5, dims, str, box);
+  } else if (smode == 2) {
+    const cuuint64_t cs = d->stride, C2 = (cuuint64_t)d->Cin * 2;
+    cuuint64_t dims[5] = {cs * d->Cin, (cuuint64_t)d->W / cs, cs, (cuuint64_t)d->H / cs, (cuuint64_t)d->B};
+    cuuint64_t str[4] = {cs * C2, (cuuint64_t)d->W * C2, cs * d->W * C2, (cuuint64_t)d->H * d->W * C2};
+    cuuint32_t box[5] = {TC_BK, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH, 1};
+    rc = make_map(&map_a, x, 5, dims, str, box);
+  } else if (p.flat) {
     cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)P};
     cuuint64_t str[1] = {(cuuint64_t)d->ldx * 2};
     cuuint32_t box[2] = {TC_BK, TC_BM};
@@ -797,7 +844,7 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
   // The persistent halo kernel wins whenever one 128-wide N tile covers the output (measured: decoder forward
   // convs 7.9 -> 4.6 ms, depth-head convs 0.8 -> 0.5 ms); the wide-N data gradients of the dense blocks
   // (136..296 output channels, K = 9 * 64..128) stay on the plain kernel (8.6 vs 9.7 ms).
-  if (use_halo && d->KH == 3 && d->H % 16 == 0 && d->W >= 16 && d->Cout <= 128 && d->Cin >= 32) {
+  if (use_halo && !smode && d->KH == 3 && d->H % 16 == 0 && d->W >= 16 && d->Cout <= 128 && d->Cin >= 32) {
     const int num_sms = sm_count();
     static unsigned long long attr_halo = 0;
     if (int e = ensure_smem_attr(conv_tc_halo_kernel, 227 * 1024, attr_halo)) return e;
@@ -852,7 +899,7 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
     CRD_LAUNCH_CHECK();
     return 0;
   }
-  const int gx = p.flat ? crd_div_up(P, TC_BM) : p.tiles_w * p.tiles_h * d->B;
+  const int gx = p.flat ? crd_div_up(P, TC_BM) : p.tiles_w * p.tiles_h * Bt;
   // N tiles of equal width <= 256 (one pass over A per tile; rows past Cout are zero-filled by TMA)
   int ntile = (d->Cout + 255) / 256;
   if (!am) {
@@ -915,6 +962,7 @@ struct WgParams {
   int halo;                 // 3x3: one X box with TH+2 rows per (chunk, kw); the kh taps are its 2-KiB row offsets
   int cpc;                  // 1x1: 64-channel chunks of X per CTA (3, or fewer when the launch would not fill the GPU)
   int bias;                 // 1x1 only: also produce db[co] = sum_px dY (an extra N=64 MMA against a tile of ones)
+  int smode, cstride, kwg;  // strided convs through the 5-D X maps of the forward kernel; kwg = groups of <= 3 kw taps
   long long Ktot;           // row stride of dw
 };
 
@@ -948,11 +996,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // work column: (chunk, kh) for KxK; a group of up to 3 chunks for 1x1
-  int c0, kh = 0, nblk;       // in halo mode `kh` holds the CTA's kw and the N blocks are the three kh taps
+  int c0, kh = 0, nblk, kw0 = 0;   // in halo mode `kh` holds the CTA's kw and the N blocks are the three kh taps
   // blockIdx.x = work column (fastest varying), blockIdx.y = pixel split: the CTAs resident at the same time
   // cover ALL columns of a few pixel ranges, so a dY / X tile fetched from HBM by one column is an L2 hit for
   // the others (with the split index fastest, each wave of columns re-streamed both tensors: 5.5x the bytes)
-  if (p.KH > 1) {
+  if (p.smode) {
+    int t = blockIdx.x;
+    const int kwgi = t % p.kwg; t /= p.kwg;
+    kh = t % p.KH;
+    c0 = (t / p.KH) * 64;
+    kw0 = kwgi * 3;
+    nblk = min(3, p.KW - kw0);
+  } else if (p.KH > 1) {
     const int chunk = blockIdx.x / p.KH;
     kh = blockIdx.x - chunk * p.KH;
     c0 = chunk * 64;
@@ -1021,7 +1076,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             const int oh0 = th * p.TH, ow0 = tw * p.TW;
             for (int j = 0; j < mblocks; j++)
               tma_load_4d(sa + j * WG_BLK_BYTES, &map_dy, bar, co0 + 64 * j, ow0, oh0, bb);
-            if (p.halo) {
+            if (p.smode == 1) {
+              for (int j = 0; j < nblk; j++)
+                tma_load_5d(sb + j * WG_BLK_BYTES, &map_x, bar, c0, kw0 + j, ow0, kh, oh0);
+            } else if (p.smode == 2) {
+              const int th_ = kh - p.pad;
+              const int dh = th_ >= 0 ? th_ / p.cstride : -((-th_ + p.cstride - 1) / p.cstride);
+              const int ph_ = th_ - dh * p.cstride;
+              for (int j = 0; j < nblk; j++) {
+                const int tw_ = kw0 + j - p.pad;
+                const int dw = tw_ >= 0 ? tw_ / p.cstride : -((-tw_ + p.cstride - 1) / p.cstride);
+                const int pw_ = tw_ - dw * p.cstride;
+                tma_load_5d(sb + j * WG_BLK_BYTES, &map_x, bar, pw_ * p.Cin + c0, ow0 + dw, ph_, oh0 + dh, bb);
+              }
+            } else if (p.halo) {
               tma_load_4d(sb, &map_x, bar, c0, ow0 + kh - p.pad, oh0 - p.pad, bb);       // kh == this CTA's kw
             } else {
               for (int j = 0; j < nblk; j++)
@@ -1071,7 +1139,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         int cc;
         if (p.KH > 1) {
           cc = c0 + col;
-          kbase = (long long)(p.halo ? (j * p.KW + kh) : (kh * p.KW + j)) * p.Cin + cc;
+          kbase = (long long)(p.halo ? (j * p.KW + kh) : (kh * p.KW + kw0 + j)) * p.Cin + cc;
         }
         else { cc = c0 + 64 * j + col; kbase = cc; }
         float* dst = dw + (long long)co * p.Ktot + kbase;
@@ -1110,10 +1178,20 @@ static int conv_wgrad_tc_impl(const crd_conv_desc* d, const void* x, const void*
   CRD_REQUIRE(d && x && dy && dw);
   CRD_REQUIRE(db == nullptr || d->KH == 1);              // the fused bias reduction exists for 1x1 contractions
   CRD_REQUIRE(d->in_dtype == CRD_BF16 && d->out_dtype == CRD_BF16);
-  CRD_REQUIRE(d->stride == 1 && !d->transposed && d->Ho == d->H && d->Wo == d->W);
+  CRD_REQUIRE(d->stride >= 1 && !d->transposed);
   CRD_REQUIRE(d->Cin % 8 == 0 && d->ldx % 8 == 0 && d->ldy % 8 == 0);
   CRD_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0);
-  CRD_REQUIRE(d->KH == d->KW && 2 * d->pad == d->KH - 1 && d->KW <= 3);
+  CRD_REQUIRE(d->KH == d->KW);
+  int smode = 0;
+  if (d->stride > 1) {
+    const int cs = d->stride;
+    CRD_REQUIRE(d->H % cs == 0 && d->W % cs == 0 && d->ldx == d->Cin && d->Ho == d->H / cs && d->Wo == d->W / cs);
+    if (d->KH == cs && d->pad == 0) smode = 1;
+    else if (d->KH == 3 && cs == 2 && d->pad == 1 && d->Cin % 64 == 0) smode = 2;
+    else return -1998;
+  } else {
+    CRD_REQUIRE(d->Ho == d->H && d->Wo == d->W && 2 * d->pad == d->KH - 1 && d->KW <= 3);
+  }
   const long long P = (long long)d->B * d->H * d->W;
   if (P == 0) return 0;
   static int WG_PIX = 0;
@@ -1132,7 +1210,8 @@ static int conv_wgrad_tc_impl(const crd_conv_desc* d, const void* x, const void*
     attr_wg = m1 & m2 & m3;
   }
   WgParams p;
-  p.flat = (d->KH == 1);
+  p.flat = (d->KH == 1 && !smode);
+  p.smode = smode; p.cstride = d->stride; p.kwg = smode ? (d->KW + 2) / 3 : 1;
   p.KH = d->KH; p.KW = d->KW; p.pad = d->pad;
   p.Cin = d->Cin; p.Cout = d->Cout;
   p.kchunks = (d->Cin + 63) / 64;
@@ -1140,13 +1219,16 @@ static int conv_wgrad_tc_impl(const crd_conv_desc* d, const void* x, const void*
   p.Ktot = (long long)d->KH * d->KW * d->Cin;
   static int wg_halo = -1;
   if (wg_halo < 0) { const char* e = getenv("CAMRADEPTH_WG_HALO"); wg_halo = (e && e[0] == '0') ? 0 : 1; }
-  p.halo = (wg_halo && d->KH == 3 && d->W >= 16) ? 1 : 0;
+  p.halo = (wg_halo && !smode && d->KH == 3 && d->W >= 16) ? 1 : 0;
   p.bias = db != nullptr;
-  p.TW = d->W >= 16 ? 16 : (d->W >= 8 ? 8 : 4);
+  // pixel tiles run over the OUTPUT image (smode 1: one image of B*Ho rows, the (b, oh) axis of the 5-D X map)
+  const int Wt = smode ? d->Wo : d->W, Ht = smode == 1 ? d->B * d->Ho : (smode == 2 ? d->Ho : d->H);
+  const int Bt = smode == 1 ? 1 : d->B;
+  p.TW = Wt >= 16 ? 16 : (Wt >= 8 ? 8 : 4);
   p.TH = WG_PIX / p.TW;
-  p.tiles_w = (d->W + p.TW - 1) / p.TW;
-  p.tiles_h = (d->H + p.TH - 1) / p.TH;
-  p.total_tiles = p.flat ? (P + WG_PIX - 1) / WG_PIX : (long long)p.tiles_w * p.tiles_h * d->B;
+  p.tiles_w = (Wt + p.TW - 1) / p.TW;
+  p.tiles_h = (Ht + p.TH - 1) / p.TH;
+  p.total_tiles = p.flat ? (P + WG_PIX - 1) / WG_PIX : (long long)p.tiles_w * p.tiles_h * Bt;
   CUtensorMap map_dy, map_x;
   int rc;
   if (p.flat) {
@@ -1158,6 +1240,24 @@ static int conv_wgrad_tc_impl(const crd_conv_desc* d, const void* x, const void*
     cuuint64_t dims2[2] = {(cuuint64_t)d->Cin, (cuuint64_t)P};
     cuuint64_t str2[1] = {(cuuint64_t)d->ldx * 2};
     rc = make_map(&map_x, x, 2, dims2, str2, box);
+  } else if (smode) {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)Wt, (cuuint64_t)Ht, (cuuint64_t)Bt};
+    cuuint64_t str[3] = {(cuuint64_t)d->ldy * 2, (cuuint64_t)Wt * d->ldy * 2, (cuuint64_t)Ht * Wt * d->ldy * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    rc = make_map(&map_dy, dy, 4, dims, str, box);
+    if (rc) return rc;
+    const cuuint64_t cs = d->stride, C2 = (cuuint64_t)d->Cin * 2;
+    if (smode == 1) {
+      cuuint64_t dx5[5] = {(cuuint64_t)d->Cin, cs, (cuuint64_t)d->W / cs, cs, (cuuint64_t)d->B * (d->H / cs)};
+      cuuint64_t sx5[4] = {C2, cs * C2, (cuuint64_t)d->W * C2, cs * d->W * C2};
+      cuuint32_t bx5[5] = {64, 1, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH};
+      rc = make_map(&map_x, x, 5, dx5, sx5, bx5);
+    } else {
+      cuuint64_t dx5[5] = {cs * d->Cin, (cuuint64_t)d->W / cs, cs, (cuuint64_t)d->H / cs, (cuuint64_t)d->B};
+      cuuint64_t sx5[4] = {cs * C2, (cuuint64_t)d->W * C2, cs * d->W * C2, (cuuint64_t)d->H * d->W * C2};
+      cuuint32_t bx5[5] = {64, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH, 1};
+      rc = make_map(&map_x, x, 5, dx5, sx5, bx5);
+    }
   } else {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
     cuuint64_t str[3] = {(cuuint64_t)d->ldy * 2, (cuuint64_t)d->W * d->ldy * 2, (cuuint64_t)d->H * d->W * d->ldy * 2};
@@ -1177,7 +1277,7 @@ static int conv_wgrad_tc_impl(const crd_conv_desc* d, const void* x, const void*
     const long long gz0 = (d->Cout + 127) / 128, sms0 = sm_count();
     while (p.cpc > 1 && ((p.kchunks + p.cpc - 1) / p.cpc) * gz0 * ((p.total_tiles + 3) / 4) < sms0) p.cpc--;
   }
-  const int gy = p.flat ? (p.kchunks + p.cpc - 1) / p.cpc : p.kchunks * p.KH;
+  const int gy = p.flat ? (p.kchunks + p.cpc - 1) / p.cpc : p.kchunks * p.KH * p.kwg;
   const int gz = (d->Cout + 127) / 128;
   // Split-K over the pixel tiles.  One CTA per SM is resident (200 KB ring), so the launch runs in waves of
   // sm_count CTAs: pick the split count minimising waves * (tiles per CTA + fixed prologue/epilogue cost, in

@@ -96,6 +96,7 @@ class Engine:
         # the GroupNorm reduction in that read-out costs more (+33 us at stage 2) than a separate statistics pass
         # over the bf16 output (~20 us), so it is fused only up to this many output channels
         self.gn_epilogue_max_cout = int(os.environ.get("CAMRADEPTH_GN_EPILOGUE_MAXN", "256"))
+        self.strided_igemm = os.environ.get("CAMRADEPTH_STRIDED_IGEMM", "1") == "1"
         # Deterministic forward: every GroupNorm statistic comes from the one-launch kernel, whose reduction order is
         # fixed (per-thread strides, shared-memory tree, no atomics), at any tensor size; the conv read-out sums
         # (fp32 atomics across CTAs) are not used.  The forward pass is then bit-reproducible run to run and
@@ -268,8 +269,19 @@ class Engine:
                 2 * L["pad"] == L["k"] - 1 and x.dtype == torch.bfloat16)
 
     def _gemm_route(self, L, x):
-        """strided convs (patch embeddings, spatial-reduction convs) on the tensor-core path: im2col + GEMM"""
+        """strided convs without an implicit-GEMM form on the tensor-core path (pe1: k7 s4 on 8 channels; Cin not a
+        multiple of 64 for k3 s2) and every strided data gradient: im2col + GEMM (+ col2im)"""
         return self.use_tc and self.tdtype == torch.bfloat16 and L["stride"] > 1 and x.dtype == torch.bfloat16
+
+    def _strided_tc(self, L, x):
+        """Strided conv as implicit GEMM: the 5-D tensor maps of crd_conv_fwd_tc / crd_conv_wgrad_tc address the taps
+        of a strided window directly (k == stride spatial-reduction convs; k3 s2 p1 patch embeddings)."""
+        if not (self.use_tc and self.strided_igemm and self.tdtype == torch.bfloat16 and x.dtype == torch.bfloat16):
+            return False
+        k, st, pad = L["k"], L["stride"], L["pad"]
+        if st <= 1 or x.shape[1] % st or x.shape[2] % st or ops._ld(x) != L["cin_p"]:
+            return False
+        return (k == st and pad == 0) or (k == 3 and st == 2 and pad == 1 and L["cin_p"] % 64 == 0)
 
     def _im2col(self, L, x, Ho, Wo):
         col = self._empty(x.shape[0], Ho, Wo, L["taps"] * L["cin_p"])
@@ -284,7 +296,7 @@ class Engine:
         w = self.wpack(name, 0)
         fuse_gn = gn and self.fuse_gn_stats and act == 0 and not accumulate and \
             (L["k"] > 1 or L["cout"] <= self.gn_epilogue_max_cout)
-        if self._gemm_route(L, x) and not out_nchw:
+        if self._gemm_route(L, x) and not out_nchw and not self._strided_tc(L, x):
             col = self._im2col(L, x, y.shape[1], y.shape[2])
             d = ops.make_desc(col, y, col.shape[-1], L["cout"], 1, 1, 1, 0, 0, act, accumulate, 0)
             sums = self.fwd_arena.take(x.shape[0], L["cout"], 2) if fuse_gn else None
@@ -294,7 +306,7 @@ class Engine:
                           out_nchw)
         b = None if bias is None else self.P[bias].detach()
         ev = self._timed("fwd", name)
-        tc = self.use_tc and self._tc_ok(L, x, y)
+        tc = self.use_tc and (self._tc_ok(L, x, y) or self._strided_tc(L, x))
         sums = self.fwd_arena.take(x.shape[0], L["cout"], 2) if (fuse_gn and tc) else None
         ops.conv_fwd(d, x, w, b, y, use_tc=tc, gn_sums=sums)
         if ev is not None:
@@ -325,7 +337,7 @@ class Engine:
         g = self.pg[name]
         dwp = g.view(L["cout"], L["cin"]) if direct else self.bwd_arena.take(L["cout"], L["taps"] * L["cin_p"])
         db = self.pg[bias] if bias is not None else None
-        if self._gemm_route(L, x) and self.use_tc_wgrad:
+        if self._gemm_route(L, x) and self.use_tc_wgrad and not self._strided_tc(L, x):
             col = self._im2col(L, x, dy.shape[1], dy.shape[2])      # recomputed: cheaper than keeping it alive
             d = ops.make_desc(col, dy, col.shape[-1], L["cout"], 1, 1, 1, 0)
             ops.conv_wgrad(d, col, dy, dwp, use_tc=True, db=db)     # bias gradient from the same pass over dy
@@ -333,7 +345,7 @@ class Engine:
         else:
             d = ops.make_desc(x, dy, L["cin_p"], L["cout"], L["k"], L["k"], L["stride"], L["pad"], 0, 0, 0, 0)
             ev = self._timed("wgrad", name)
-            tc = self.use_tc_wgrad and self._tc_ok(L, x, dy)
+            tc = self.use_tc_wgrad and (self._tc_ok(L, x, dy) or self._strided_tc(L, x))
             fused = tc and L["k"] == 1 and db is not None
             ops.conv_wgrad(d, x, dy, dwp, use_tc=tc, db=db if fused else None)
             if fused:

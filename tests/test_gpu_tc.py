@@ -185,3 +185,52 @@ def test_conv_argmax_fused(case):
     assert torch.equal(buf0[..., 128], want) and torch.equal(buf1[..., 3], want)
     assert float((buf0[..., :128] - 7).abs().max()) == 0 and float((buf0[..., 129:] - 7).abs().max()) == 0
     assert float((buf1[..., :3] - 7).abs().max()) == 0 and float((buf1[..., 4:] - 7).abs().max()) == 0
+
+
+STRIDED_CASES = [
+    # B, Cin, H, W, Cout, k, stride, pad
+    (2, 64, 48, 104, 64, 8, 8, 0),       # stage-1 spatial-reduction conv (simplified_attention.py:68)
+    (2, 128, 24, 52, 128, 4, 4, 0),      # stage 2
+    (3, 160, 12, 26, 160, 2, 2, 0),      # stage 3: ragged last 64-channel chunk, tiles cross sample boundaries
+    (2, 64, 48, 104, 128, 3, 2, 1),      # patch_embed2 (k3 s2 p1, :158-160)
+    (1, 128, 24, 52, 160, 3, 2, 1),      # patch_embed3
+    (2, 64, 16, 16, 96, 2, 2, 0),
+]
+
+
+@pytest.mark.parametrize("case", STRIDED_CASES)
+def test_conv_tc_strided_implicit_gemm(case):
+    """Strided convolutions straight from the NHWC tensor through 5-D tensor maps (no im2col buffer): forward with
+    bias and GroupNorm sums, and the weight gradient, against F.conv2d / autograd on the bf16-rounded operands."""
+    from camradepth_b200 import ops
+    B, Cin, H, W, Cout, k, st, pad = case
+    torch.manual_seed(0)
+    d = dev()
+    x = torch.randn(B, Cin, H, W, device=d)
+    w = torch.randn(Cout, Cin, k, k, device=d) / math.sqrt(Cin * k * k)
+    bias = torch.randn(Cout, device=d)
+    xr, wr = rnd(x, BF).requires_grad_(True), rnd(w, BF).requires_grad_(True)
+    yr = F.conv2d(xr, wr, bias, stride=st, padding=pad)
+    Ho, Wo = yr.shape[2], yr.shape[3]
+    xb = nhwc(x, BF)
+    wp = torch.zeros(Cout, k * k * Cin, dtype=BF, device=d)
+    ops.weight_pack(w, wp, None, Cout, Cin, k * k, Cin, r8(Cout), 0)
+    ybuf = torch.zeros(B, Ho, Wo, Cout + 16, dtype=BF, device=d)
+    y = ybuf[..., 8:8 + Cout]
+    sums = torch.zeros(B, Cout, 2, device=d)
+    ops.conv_fwd(ops.make_desc(xb, y, Cin, Cout, k, k, st, pad), xb, wp, bias, y, use_tc=True, gn_sums=sums)
+    torch.cuda.synchronize()
+    assert rel(nchw(y, Cout), yr) < 5e-3, rel(nchw(y, Cout), yr)
+    assert float(ybuf[..., :8].abs().max()) == 0 and float(ybuf[..., 8 + Cout:].abs().max()) == 0
+    yd = yr.detach().double()
+    assert rel(sums[..., 0], yd.sum((2, 3))) < 2e-4 and rel(sums[..., 1], (yd * yd).sum((2, 3))) < 1e-4
+    # weight gradient
+    gy = torch.randn_like(yr)
+    (gw_ref,) = torch.autograd.grad(yr, (wr,), rnd(gy, BF))
+    dy = nhwc(gy, BF)
+    dwp = torch.zeros(Cout, k * k * Cin, dtype=torch.float32, device=d)
+    ops.conv_wgrad(ops.make_desc(xb, dy, Cin, Cout, k, k, st, pad), xb, dy, dwp, use_tc=True)
+    gw = torch.empty_like(w)
+    ops.weight_unpack_grad(dwp, gw, None, Cout, Cin, k * k, Cin, False)
+    torch.cuda.synchronize()
+    assert rel(gw, gw_ref) < 1e-3, rel(gw, gw_ref)
