@@ -52,6 +52,7 @@ __device__ __forceinline__ float bc_weight(int o, int s, int n) {
 template <bool BWD>
 __global__ void __launch_bounds__(BC_THREADS, 2)
 bicubic_tma_kernel(const __grid_constant__ CUtensorMap m_in, const BcParams p) {
+  CRD_PDL_ENTRY();
   constexpr int RH = BWD ? 8 : 5;                // rows per box = register-window depth
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -300,7 +301,7 @@ inline int bc_tma_launch(const void* in, BcParams p, cudaStream_t st) {
   cuuint64_t str[3] = {(cuuint64_t)p.ld_in * 2, (cuuint64_t)Wi * p.ld_in * 2, (cuuint64_t)Hi * Wi * p.ld_in * 2};
   cuuint32_t box[4] = {DW_CH, (cuuint32_t)(wmul * p.TW + halo), (cuuint32_t)RH, 1};
   if (int e = make_map(&m_in, in, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
-  bicubic_tma_kernel<BWD><<<p.cta_begin[p.ntiles], BC_THREADS, smem, st>>>(m_in, p);
+  crd_launch(bicubic_tma_kernel<BWD>, dim3(p.cta_begin[p.ntiles]), dim3(BC_THREADS), smem, st, m_in, p);
   return 0;
 }
 

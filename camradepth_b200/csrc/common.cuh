@@ -20,6 +20,36 @@ extern unsigned long long g_crd_launches;   // counted by every launcher (crd_la
 
 typedef __nv_bfloat16 bf16;
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// The training step is ~1800 mostly tiny, strictly ordered kernels.  A kernel launched through crd_launch carries the
+// programmatic-stream-serialization attribute: its CTAs may be scheduled (and run their prologue: barrier init,
+// tensor-map prefetch, TMEM allocation) while the previous kernel in the stream is still draining, and block in
+// pdl_wait() until that kernel has completed and its memory is visible.  Every such kernel calls
+// pdl_launch_dependents() first (lets ITS successor be scheduled early; always safe because the successor waits for
+// full completion) and pdl_wait() before its first global-memory access.  Without the attribute both are no-ops.
+// In a captured CUDA graph the attribute becomes a programmatic dependency edge.  CAMRADEPTH_PDL=0 disables.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#define CRD_PDL_ENTRY() do { pdl_launch_dependents(); pdl_wait(); } while (0)
+
+bool crd_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t crd_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = crd_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <typename T> struct TypeTag;
 template <> struct TypeTag<float> { static constexpr int id = CRD_F32; };
 template <> struct TypeTag<bf16> { static constexpr int id = CRD_BF16; };

@@ -27,6 +27,7 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 template <typename T>
 __global__ void bicubic_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C,
                                    int ldx, int ldy) {
+  CRD_PDL_ENTRY();
   const int cvec = C / 8;
   const int Ho = 2 * H, Wo = 2 * W;
   const long long total = (long long)B * Ho * Wo * cvec;
@@ -75,6 +76,7 @@ __device__ __forceinline__ float bicubic_weight(int o, int s, int n) {
 template <typename T>
 __global__ void bicubic_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int accumulate, int B, int H,
                                    int W, int C, int lddy, int lddx) {
+  CRD_PDL_ENTRY();
   const int cvec = C / 8;
   const int Ho = 2 * H, Wo = 2 * W;
   const long long total = (long long)B * H * W * cvec;
@@ -129,6 +131,7 @@ template <typename T>
 __global__ void conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                    const float* __restrict__ bias, float* __restrict__ y, int B, int H, int W,
                                    int Cin, int ldx) {
+  CRD_PDL_ENTRY();
   extern __shared__ float ws[];   // [9][Cin]
   for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
@@ -167,6 +170,7 @@ __global__ void conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restr
 template <typename T>
 __global__ void conv_c1_bwd_input_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                          T* __restrict__ dx, int B, int H, int W, int Cin, int lddx) {
+  CRD_PDL_ENTRY();
   const int cvec = Cin / 8;
   const long long total = (long long)B * H * W * cvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -198,6 +202,7 @@ __global__ void conv_c1_bwd_input_kernel(const float* __restrict__ dy, const flo
 template <typename T>
 __global__ void conv_c1_bwd_weight_kernel(const float* __restrict__ dy, const T* __restrict__ x, float* dw,
                                           float* db, int B, int H, int W, int Cin, int ldx, long long ppb) {
+  CRD_PDL_ENTRY();
   extern __shared__ float red[];
   const int cv = threadIdx.x, ry = threadIdx.y, rows = blockDim.y, cvec = blockDim.x;
   const int b = blockIdx.y;
@@ -252,6 +257,7 @@ __global__ void conv_c1_bwd_weight_kernel(const float* __restrict__ dy, const T*
 template <typename T>
 __global__ void sigmoid_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx,
                                    long long n8) {
+  CRD_PDL_ENTRY();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
        i += (long long)gridDim.x * blockDim.x) {
     float g[8], s[8];
@@ -266,6 +272,7 @@ __global__ void sigmoid_bwd_kernel(const T* __restrict__ dy, const T* __restrict
 template <typename T, typename TD>
 __global__ void argmax_map_kernel(const T* __restrict__ logits, int ld, int ncls, TD* dst, int ld_dst,
                                   float* dst_f32, long long npix) {
+  CRD_PDL_ENTRY();
   for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
        pix += (long long)gridDim.x * blockDim.x) {
     const T* lp = logits + pix * ld;
@@ -285,6 +292,7 @@ __global__ void argmax_map_kernel(const T* __restrict__ logits, int ld, int ncls
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int B, int C, int H,
                                     int W, int ld) {
+  CRD_PDL_ENTRY();
   const long long hw = (long long)H * W;
   const long long total = (long long)B * hw;
   for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
@@ -296,6 +304,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int B, int C, int H,
                                     int W, int ld) {
+  CRD_PDL_ENTRY();
   const long long hw = (long long)H * W;
   const long long total = (long long)B * hw;
   for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
@@ -308,6 +317,7 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict
 template <typename T>
 __global__ void weight_pack_kernel(const float* __restrict__ w, T* __restrict__ dst, const int* __restrict__ map,
                                    int Cout, int Cin, int taps, int Cin_p, int Cout_p, int mode) {
+  CRD_PDL_ENTRY();
   const long long total = (long long)Cout * Cin * taps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -325,6 +335,7 @@ __global__ void weight_pack_kernel(const float* __restrict__ w, T* __restrict__ 
 // training step).  table: n+1 rows of 12 int64 {w, dst, map, first block, Cout, Cin, taps, Cin_p, Cout_p, mode,
 // dst dtype, elements}; row n carries the total block count.  One block packs 1024 consecutive source elements.
 __global__ void __launch_bounds__(256) weight_pack_batch_kernel(const long long* __restrict__ table, int n) {
+  CRD_PDL_ENTRY();
   __shared__ int item;
   if (threadIdx.x == 0) {
     int lo = 0, hi = n;                          // last row whose first block <= blockIdx.x
@@ -360,6 +371,7 @@ __global__ void __launch_bounds__(256) weight_pack_batch_kernel(const long long*
 __global__ void weight_unpack_grad_kernel(const float* __restrict__ dwp, float* __restrict__ grad,
                                           const int* __restrict__ map, int Cout, int Cin, int taps, int Cin_p,
                                           int accumulate) {
+  CRD_PDL_ENTRY();
   const long long total = (long long)Cout * Cin * taps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -377,6 +389,7 @@ __global__ void weight_unpack_grad_kernel(const float* __restrict__ dwp, float* 
 template <typename T>
 __global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ col, int B, int H, int W, int Cin, int ldx,
                               int Ho, int Wo, int KH, int KW, int stride, int pad) {
+  CRD_PDL_ENTRY();
   const int cvec = Cin / 8;
   const int taps = KH * KW;
   const long long total = (long long)B * Ho * Wo * taps * cvec;
@@ -402,6 +415,7 @@ __global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ col, int 
 template <typename T>
 __global__ void col2im_kernel(const T* __restrict__ dcol, T* __restrict__ dx, int accumulate, int B, int H, int W,
                               int Cin, int lddx, int Ho, int Wo, int KH, int KW, int stride, int pad) {
+  CRD_PDL_ENTRY();
   const int cvec = Cin / 8;
   const int taps = KH * KW;
   const long long total = (long long)B * H * W * cvec;
@@ -446,6 +460,7 @@ __global__ void col2im_kernel(const T* __restrict__ dcol, T* __restrict__ dx, in
 // db[n] += sum_m dy[m][n]; blockDim = (cvec, rows)
 template <typename T>
 __global__ void col_sum_kernel(const T* __restrict__ dy, float* db, long long M, int N, int ld, long long ppb) {
+  CRD_PDL_ENTRY();
   extern __shared__ float red[];
   const int cv = threadIdx.x, ry = threadIdx.y, rows = blockDim.y, cvec = blockDim.x;
   long long p0 = (long long)blockIdx.x * ppb, p1 = p0 + ppb;
@@ -484,7 +499,7 @@ extern "C" int crd_bicubic2x_fwd(const void* x, void* y, int dtype, int B, int H
     CRD_LAUNCH_CHECK();
     return 0;
   }
-  CRD_DISPATCH_1(dtype, T, bicubic_fwd_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dtype, T, crd_launch(bicubic_fwd_kernel<T>, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, 
                                (const T*)x, (T*)y, B, H, W, C, ldx, ldy));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -501,7 +516,7 @@ extern "C" int crd_bicubic2x_bwd(const void* dy, void* dx, int dtype, int accumu
     CRD_LAUNCH_CHECK();
     return 0;
   }
-  CRD_DISPATCH_1(dtype, T, bicubic_bwd_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dtype, T, crd_launch(bicubic_bwd_kernel<T>, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, 
                                (const T*)dy, (T*)dx, accumulate, B, H, W, C, lddy, lddx));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -511,8 +526,7 @@ extern "C" int crd_conv3x3_c1_fwd(const void* x, int dtype, const float* w, cons
   CRD_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0 && Cin <= 1024);
   const long long total = (long long)B * H * W;
   if (total == 0) return 0;
-  CRD_DISPATCH_1(dtype, T, conv_c1_fwd_kernel<T><<<ew_blocks(total), 256, 9 * Cin * sizeof(float),
-                                                   (cudaStream_t)stream>>>((const T*)x, w, bias, y, B, H, W, Cin, ldx));
+  CRD_DISPATCH_1(dtype, T, crd_launch(conv_c1_fwd_kernel<T>, dim3(ew_blocks(total)), dim3(256), 9 * Cin * sizeof(float), (cudaStream_t)stream, (const T*)x, w, bias, y, B, H, W, Cin, ldx));
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -524,14 +538,14 @@ extern "C" int crd_conv3x3_c1_bwd(const float* dy, const void* x, int dtype, con
   if (total == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (dx) {
-    CRD_DISPATCH_1(dtype, T, conv_c1_bwd_input_kernel<T><<<ew_blocks(total), 256, 0, s>>>(
+    CRD_DISPATCH_1(dtype, T, crd_launch(conv_c1_bwd_input_kernel<T>, dim3(ew_blocks(total)), dim3(256), 0, s, 
                                  dy, w, (T*)dx, B, H, W, Cin, lddx));
     CRD_LAUNCH_CHECK();
   }
   if (dw) {
     ReduceLaunch r = plan_reduce(B, (long long)H * W, Cin);
     const size_t smem = (size_t)r.block.x * r.block.y * 8 * sizeof(float);
-    CRD_DISPATCH_1(dtype, T, conv_c1_bwd_weight_kernel<T><<<r.grid, r.block, smem, s>>>(
+    CRD_DISPATCH_1(dtype, T, crd_launch(conv_c1_bwd_weight_kernel<T>, dim3(r.grid), dim3(r.block), smem, s, 
                                  dy, (const T*)x, dw, db, B, H, W, Cin, ldx, r.ppb));
     CRD_LAUNCH_CHECK();
   }
@@ -541,7 +555,7 @@ extern "C" int crd_sigmoid_bwd(const void* dy, const void* y, void* dx, int dtyp
                                crd_stream_t stream) {
   CRD_REQUIRE(n % 8 == 0);
   if (n == 0) return 0;
-  CRD_DISPATCH_1(dtype, T, sigmoid_bwd_kernel<T><<<ew_blocks(n / 8), 256, 0, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dtype, T, crd_launch(sigmoid_bwd_kernel<T>, dim3(ew_blocks(n / 8)), dim3(256), 0, (cudaStream_t)stream, 
                                (const T*)dy, (const T*)y, (T*)dx, n / 8));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -551,6 +565,7 @@ namespace {
 template <typename T>
 __global__ void copy_channels_kernel(const T* __restrict__ src, int ld_src, T* __restrict__ dst, int ld_dst, int C,
                                      long long npix) {
+  CRD_PDL_ENTRY();
   for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
        pix += (long long)gridDim.x * blockDim.x) {
     const T* s = src + pix * ld_src;
@@ -563,7 +578,7 @@ extern "C" int crd_copy_channels(const void* src, int ld_src, void* dst, int ld_
                                  crd_stream_t stream) {
   CRD_REQUIRE(src && dst && C >= 0);
   if (npix == 0 || C == 0) return 0;
-  CRD_DISPATCH_1(dtype, T, copy_channels_kernel<T><<<ew_blocks(npix), 256, 0, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dtype, T, crd_launch(copy_channels_kernel<T>, dim3(ew_blocks(npix)), dim3(256), 0, (cudaStream_t)stream, 
                                (const T*)src, ld_src, (T*)dst, ld_dst, C, npix));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -572,7 +587,7 @@ extern "C" int crd_argmax_map(const void* logits, int dtype, int ld, int ncls, v
                               int ld_dst, float* dst_f32, long long npix, crd_stream_t stream) {
   if (npix == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  CRD_DISPATCH_1(dtype, T, CRD_DISPATCH_1(dst_dtype, TD, argmax_map_kernel<T, TD><<<ew_blocks(npix), 256, 0, s>>>(
+  CRD_DISPATCH_1(dtype, T, CRD_DISPATCH_1(dst_dtype, TD, crd_launch(argmax_map_kernel<T, TD>, dim3(ew_blocks(npix)), dim3(256), 0, s, 
                                (const T*)logits, ld, ncls, (TD*)dst, ld_dst, dst_f32, npix)));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -581,7 +596,7 @@ extern "C" int crd_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int 
                                 int ld_dst, crd_stream_t stream) {
   const long long total = (long long)B * H * W;
   if (total == 0) return 0;
-  CRD_DISPATCH_1(dst_dtype, T, nchw_to_nhwc_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dst_dtype, T, crd_launch(nchw_to_nhwc_kernel<T>, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, 
                                    src, (T*)dst, B, C, H, W, ld_dst));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -590,7 +605,7 @@ extern "C" int crd_nhwc_to_nchw(const void* src, int src_dtype, float* dst, int 
                                 int ld_src, crd_stream_t stream) {
   const long long total = (long long)B * H * W;
   if (total == 0) return 0;
-  CRD_DISPATCH_1(src_dtype, T, nhwc_to_nchw_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(src_dtype, T, crd_launch(nhwc_to_nchw_kernel<T>, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, 
                                    (const T*)src, dst, B, C, H, W, ld_src));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -599,7 +614,7 @@ extern "C" int crd_weight_pack(const float* w, void* dst, int dst_dtype, const i
                                int taps, int Cin_p, int Cout_p, int mode, crd_stream_t stream) {
   const long long total = (long long)Cout * Cin * taps;
   if (total == 0) return 0;
-  CRD_DISPATCH_1(dst_dtype, T, weight_pack_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dst_dtype, T, crd_launch(weight_pack_kernel<T>, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, 
                                    w, (T*)dst, map, Cout, Cin, taps, Cin_p, Cout_p, mode));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -607,7 +622,7 @@ extern "C" int crd_weight_pack(const float* w, void* dst, int dst_dtype, const i
 extern "C" int crd_weight_pack_batch(const long long* table, int n_items, int n_blocks, crd_stream_t stream) {
   CRD_REQUIRE(table != nullptr || n_items == 0);
   if (n_items <= 0 || n_blocks <= 0) return 0;
-  weight_pack_batch_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>(table, n_items);
+  crd_launch(weight_pack_batch_kernel, dim3(n_blocks), dim3(256), 0, (cudaStream_t)stream, table, n_items);
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -615,7 +630,7 @@ extern "C" int crd_weight_unpack_grad(const float* dwp, float* grad, const int* 
                                       int Cin_p, int accumulate, crd_stream_t stream) {
   const long long total = (long long)Cout * Cin * taps;
   if (total == 0) return 0;
-  weight_unpack_grad_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(dwp, grad, map, Cout, Cin, taps,
+  crd_launch(weight_unpack_grad_kernel, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, dwp, grad, map, Cout, Cin, taps,
                                                                                Cin_p, accumulate);
   CRD_LAUNCH_CHECK();
   return 0;
@@ -625,7 +640,7 @@ extern "C" int crd_im2col(const void* x, void* col, int dtype, int B, int H, int
   CRD_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0);
   const long long total = (long long)B * Ho * Wo * KH * KW * (Cin / 8);
   if (total == 0) return 0;
-  CRD_DISPATCH_1(dtype, T, im2col_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dtype, T, crd_launch(im2col_kernel<T>, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, 
                                (const T*)x, (T*)col, B, H, W, Cin, ldx, Ho, Wo, KH, KW, stride, pad));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -635,7 +650,7 @@ extern "C" int crd_col2im(const void* dcol, void* dx, int dtype, int accumulate,
   CRD_REQUIRE(Cin % 8 == 0 && lddx % 8 == 0);
   const long long total = (long long)B * H * W * (Cin / 8);
   if (total == 0) return 0;
-  CRD_DISPATCH_1(dtype, T, col2im_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dtype, T, crd_launch(col2im_kernel<T>, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, 
                                (const T*)dcol, (T*)dx, accumulate, B, H, W, Cin, lddx, Ho, Wo, KH, KW, stride, pad));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -647,7 +662,7 @@ extern "C" int crd_col_sum(const void* dy, int dtype, float* db, long long M, in
   CRD_REQUIRE(Np <= ld && Np / 8 <= 256);
   ReduceLaunch r = plan_reduce(1, M, Np);
   const size_t smem = (size_t)r.block.x * r.block.y * 8 * sizeof(float);
-  CRD_DISPATCH_1(dtype, T, col_sum_kernel<T><<<dim3(r.grid.x), r.block, smem, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dtype, T, crd_launch(col_sum_kernel<T>, dim3(dim3(r.grid.x)), dim3(r.block), smem, (cudaStream_t)stream, 
                                (const T*)dy, db, M, N, ld, r.ppb));
   CRD_LAUNCH_CHECK();
   return 0;

@@ -55,6 +55,7 @@ __device__ __forceinline__ void stg8_bf16(bf16* p, const float (&v)[4]) {
 template <bool BWD>
 __global__ void __launch_bounds__(DW_THREADS, BWD ? 1 : 2)
 dwconv_tma_kernel(const __grid_constant__ CUtensorMap m_a, const __grid_constant__ CUtensorMap m_x, const DwParams p) {
+  CRD_PDL_ENTRY();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -287,7 +288,7 @@ inline int dw_tma_launch(const void* a_in, const void* x_in, DwParams p, cudaStr
     cuuint32_t box_x[4] = {DW_CH, (cuuint32_t)p.TW, DW_RH, 1};
     if (int e = make_map(&m_x, x_in, 4, dims, str, box_x, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
   }
-  dwconv_tma_kernel<BWD><<<dim3(per_tile, ctiles), DW_THREADS, smem, st>>>(m_a, m_x, p);
+  crd_launch(dwconv_tma_kernel<BWD>, dim3(dim3(per_tile, ctiles)), dim3(DW_THREADS), smem, st, m_a, m_x, p);
   return 0;
 }
 

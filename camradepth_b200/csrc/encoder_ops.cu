@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const T* __restrict__ x
                                                          const float* __restrict__ w, const float* __restrict__ bias,
                                                          T* __restrict__ y, int B, int H, int W, int C,
                                                          long long ppb) {
+  CRD_PDL_ENTRY();
   const int c = threadIdx.x * 8, ry = threadIdx.y, rows = blockDim.y;
   const int b = blockIdx.y;
   const long long N = (long long)H * W;
@@ -64,6 +65,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) dwconv_bwd_input_kernel(const T* __restrict__ dy, const float* __restrict__ w,
                                                                T* __restrict__ dxn, int B, int H, int W, int C,
                                                                long long ppb) {
+  CRD_PDL_ENTRY();
   const int c = threadIdx.x * 8, ry = threadIdx.y, rows = blockDim.y;
   const int b = blockIdx.y;
   const long long N = (long long)H * W;
@@ -106,6 +108,7 @@ template <typename T>
 __global__ void dwconv_bwd_weight_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                          const float* __restrict__ ab, float* dw, float* db, int B, int H, int W,
                                          int C, long long ppb) {
+  CRD_PDL_ENTRY();
   extern __shared__ float red[];
   const int cv = threadIdx.x, ry = threadIdx.y, rows = blockDim.y, cvec = blockDim.x;
   const int b = blockIdx.y;
@@ -172,6 +175,7 @@ __global__ void __launch_bounds__(256, 1) dwconv_bwd_fused_kernel(const T* __res
                                                                   const float* __restrict__ w, T* __restrict__ dxn,
                                                                   float* dw, float* db, int B, int H, int W, int C,
                                                                   long long ppb) {
+  CRD_PDL_ENTRY();
   extern __shared__ float red[];
   const int cv = threadIdx.x, ry = threadIdx.y, rows = blockDim.y, cvec = blockDim.x;
   const int c = cv * 8, b = blockIdx.y;
@@ -245,6 +249,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) attn_qkmax_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k,
                                                              float* __restrict__ s, unsigned short* __restrict__ idx,
                                                              int B, int N, int M, int C, int heads, float scale) {
+  CRD_PDL_ENTRY();
   extern __shared__ float sm[];
   const int hd = C / heads;
   const int hdp = hd + 1;
@@ -302,6 +307,7 @@ __global__ void attn_qkmax_bwd_kernel(const float* __restrict__ ds, const T* __r
                                       const T* __restrict__ k, const unsigned short* __restrict__ idx,
                                       T* __restrict__ dq, float* dk, int B, int N, int M, int C, int heads,
                                       float scale) {
+  CRD_PDL_ENTRY();
   const int cvec = C / 8;
   const int hd = C / heads;
   const long long total = (long long)B * N * cvec;
@@ -334,6 +340,7 @@ __global__ void attn_qkmax_bwd_kernel(const float* __restrict__ ds, const T* __r
 // one warp per (sample, output channel): B*C warps in flight instead of B blocks walking C outputs serially
 __global__ void __launch_bounds__(256) attn_pv_fwd_kernel(const float* __restrict__ xbar, const float* __restrict__ Wp,
                                                           float* __restrict__ pv, int B, int C) {
+  CRD_PDL_ENTRY();
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o = blockIdx.x * 8 + warp;
@@ -348,6 +355,7 @@ __global__ void __launch_bounds__(256) attn_pv_fwd_kernel(const float* __restric
 }
 __global__ void attn_pv_bwd_w_kernel(const float* __restrict__ dpv, const float* __restrict__ xbar, float* dWp,
                                      int B, int C) {
+  CRD_PDL_ENTRY();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)C * C) return;
   const int o = (int)(i / C), c = (int)(i % C);
@@ -359,6 +367,7 @@ __global__ void attn_pv_bwd_w_kernel(const float* __restrict__ dpv, const float*
 // block (32 channels, 8 slices of the output-channel sum) per (channel tile, sample)
 __global__ void __launch_bounds__(256) attn_pv_bwd_x_kernel(const float* __restrict__ dpv, const float* __restrict__ Wp,
                                                             float* __restrict__ dxbar, float scale, int B, int C) {
+  CRD_PDL_ENTRY();
   __shared__ float red[8][33];
   const int cl = threadIdx.x & 31, os = threadIdx.x >> 5;
   const int b = blockIdx.y, c = blockIdx.x * 32 + cl;
@@ -382,6 +391,7 @@ __global__ void attn_out_residual_kernel(const float* __restrict__ x, const floa
                                          const float* __restrict__ s, const float* __restrict__ bp,
                                          const float* __restrict__ dp, float* __restrict__ xout, int B, int N,
                                          int C) {
+  CRD_PDL_ENTRY();
   const int c4 = C / 4;
   const long long total = (long long)B * N * c4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -406,6 +416,7 @@ __global__ void attn_out_residual_kernel(const float* __restrict__ x, const floa
 // ds[b][n] = dp[b] * sum_c dx[b][n][c] * pv[b][c]   (one warp per token)
 __global__ void attn_out_bwd_ds_kernel(const float* __restrict__ dx, const float* __restrict__ pv,
                                        const float* __restrict__ dp, float* __restrict__ ds, int B, int N, int C) {
+  CRD_PDL_ENTRY();
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= (long long)B * N) return;
@@ -421,6 +432,7 @@ __global__ void attn_out_bwd_ds_kernel(const float* __restrict__ dx, const float
 }
 __global__ void attn_out_bwd_chan_kernel(const float* __restrict__ dx, const float* __restrict__ s, float* tmp,
                                          int B, long long N, int C, long long ppb) {
+  CRD_PDL_ENTRY();
   chan_reduce2([&](int b, long long p, int c, float (&s0)[8], float (&s1)[8]) {
     float g[8];
     const long long tok = (long long)b * N + p;
@@ -432,6 +444,7 @@ __global__ void attn_out_bwd_chan_kernel(const float* __restrict__ dx, const flo
 }
 __global__ void attn_out_bwd_fin_kernel(const float* __restrict__ tmp, const float* __restrict__ dp,
                                         float* __restrict__ dpv, float* dbp, int B, int C) {
+  CRD_PDL_ENTRY();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float acc = 0.f;
@@ -447,6 +460,7 @@ template <typename T>
 __global__ void residual_add_kernel(const float* __restrict__ x, const T* __restrict__ y,
                                     const float* __restrict__ dp, float* __restrict__ xout, int B, long long N,
                                     int C) {
+  CRD_PDL_ENTRY();
   const int cvec = C / 8;
   const long long total = (long long)B * N * cvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -465,6 +479,7 @@ __global__ void residual_add_kernel(const float* __restrict__ x, const T* __rest
 template <typename T>
 __global__ void scale_cast_kernel(const float* __restrict__ dx, const float* __restrict__ dp, T* __restrict__ dy,
                                   int B, long long N, int C) {
+  CRD_PDL_ENTRY();
   const int cvec = C / 8;
   const long long total = (long long)B * N * cvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -481,6 +496,7 @@ __global__ void scale_cast_kernel(const float* __restrict__ dx, const float* __r
 }
 template <typename T>
 __global__ void add_f32_kernel(float* __restrict__ dst, const T* __restrict__ src, long long n8) {
+  CRD_PDL_ENTRY();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
        i += (long long)gridDim.x * blockDim.x) {
     float a[8], b[8];
@@ -506,7 +522,7 @@ extern "C" int crd_dwconv3x3_fwd(const void* x, int dtype, const float* ab, cons
     return 0;
   }
   ReduceLaunch r = plan_stream(B, (long long)H * W, C);
-  CRD_DISPATCH_1(dtype, T, dwconv_fwd_kernel<T><<<r.grid, r.block, 0, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dtype, T, crd_launch(dwconv_fwd_kernel<T>, dim3(r.grid), dim3(r.block), 0, (cudaStream_t)stream, 
                                (const T*)x, ab, w, bias, (T*)y, B, H, W, C, r.ppb));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -516,7 +532,7 @@ extern "C" int crd_dwconv3x3_bwd_input(const void* dy, int dtype, const float* w
   CRD_REQUIRE(C % 8 == 0 && C / 8 <= 256);
   if ((long long)B * H * W == 0) return 0;
   ReduceLaunch r = plan_stream(B, (long long)H * W, C);
-  CRD_DISPATCH_1(dtype, T, dwconv_bwd_input_kernel<T><<<r.grid, r.block, 0, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dtype, T, crd_launch(dwconv_bwd_input_kernel<T>, dim3(r.grid), dim3(r.block), 0, (cudaStream_t)stream, 
                                (const T*)dy, w, (T*)dxn, B, H, W, C, r.ppb));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -527,7 +543,7 @@ extern "C" int crd_dwconv3x3_bwd_weight(const void* dy, int dtype, const void* x
   if (B == 0 || H * W == 0) return 0;
   ReduceLaunch r = plan_reduce(B, (long long)H * W, C);
   const size_t smem = (size_t)r.block.x * r.block.y * 8 * sizeof(float);
-  CRD_DISPATCH_1(dtype, T, dwconv_bwd_weight_kernel<T><<<r.grid, r.block, smem, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dtype, T, crd_launch(dwconv_bwd_weight_kernel<T>, dim3(r.grid), dim3(r.block), smem, (cudaStream_t)stream, 
                                (const T*)dy, (const T*)x, ab, dw, db, B, H, W, C, r.ppb));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -546,7 +562,7 @@ extern "C" int crd_dwconv3x3_bwd(const void* dy, int dtype, const void* x, const
   }
   ReduceLaunch r = plan_reduce(B, (long long)H * W, C);
   const size_t smem = (size_t)r.block.x * r.block.y * 8 * sizeof(float);
-  CRD_DISPATCH_1(dtype, T, dwconv_bwd_fused_kernel<T><<<r.grid, r.block, smem, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dtype, T, crd_launch(dwconv_bwd_fused_kernel<T>, dim3(r.grid), dim3(r.block), smem, (cudaStream_t)stream, 
                                (const T*)dy, (const T*)x, ab, w, (T*)dxn, dw, db, B, H, W, C, r.ppb));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -564,7 +580,7 @@ extern "C" int crd_attn_qkmax_fwd(const void* q, const void* k, int dtype, float
   const int hd = C / heads;
   const size_t smem = (size_t)(ATN + AMK) * (hd + 1) * sizeof(float);
   dim3 grid(crd_div_up(N, ATN), B);
-  CRD_DISPATCH_1(dtype, T, attn_qkmax_fwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dtype, T, crd_launch(attn_qkmax_fwd_kernel<T>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, 
                                (const T*)q, (const T*)k, s, idx, B, N, M, C, heads, scale));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -575,23 +591,23 @@ extern "C" int crd_attn_qkmax_bwd(const float* ds, const void* q, const void* k,
   CRD_REQUIRE(heads > 0 && C % heads == 0 && (C / heads) % 8 == 0);
   const long long total = (long long)B * N * (C / 8);
   if (total == 0) return 0;
-  CRD_DISPATCH_1(dtype, T, attn_qkmax_bwd_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dtype, T, crd_launch(attn_qkmax_bwd_kernel<T>, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, 
                                ds, (const T*)q, (const T*)k, idx, (T*)dq, dk, B, N, M, C, heads, scale));
   CRD_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int crd_attn_pv_fwd(const float* xbar, const float* Wp, float* pv, int B, int C, crd_stream_t stream) {
   if (B == 0) return 0;
-  attn_pv_fwd_kernel<<<dim3(crd_div_up(C, 8), B), 256, 0, (cudaStream_t)stream>>>(xbar, Wp, pv, B, C);
+  crd_launch(attn_pv_fwd_kernel, dim3(dim3(crd_div_up(C, 8), B)), dim3(256), 0, (cudaStream_t)stream, xbar, Wp, pv, B, C);
   CRD_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int crd_attn_pv_bwd(const float* dpv, const float* xbar, const float* Wp, float* dWp, float* dxbar,
                                float dxbar_scale, int B, int C, crd_stream_t stream) {
   if (B == 0) return 0;
-  attn_pv_bwd_w_kernel<<<crd_div_up((long long)C * C, 256), 256, 0, (cudaStream_t)stream>>>(dpv, xbar, dWp, B, C);
+  crd_launch(attn_pv_bwd_w_kernel, dim3(crd_div_up((long long)C * C, 256)), dim3(256), 0, (cudaStream_t)stream, dpv, xbar, dWp, B, C);
   CRD_LAUNCH_CHECK();
-  attn_pv_bwd_x_kernel<<<dim3(crd_div_up(C, 32), B), 256, 0, (cudaStream_t)stream>>>(dpv, Wp, dxbar, dxbar_scale, B, C);
+  crd_launch(attn_pv_bwd_x_kernel, dim3(dim3(crd_div_up(C, 32), B)), dim3(256), 0, (cudaStream_t)stream, dpv, Wp, dxbar, dxbar_scale, B, C);
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -600,7 +616,7 @@ extern "C" int crd_attn_out_residual(const float* x, const float* pv, const floa
   CRD_REQUIRE(C % 4 == 0);
   const long long total = (long long)B * N * (C / 4);
   if (total == 0) return 0;
-  attn_out_residual_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, pv, s, bp, dp, xout, B, N, C);
+  crd_launch(attn_out_residual_kernel, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, x, pv, s, bp, dp, xout, B, N, C);
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -609,13 +625,13 @@ extern "C" int crd_attn_out_bwd(const float* dx, const float* pv, const float* s
   CRD_REQUIRE(C % 8 == 0 && C / 8 <= 256);
   if (B == 0 || N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  attn_out_bwd_ds_kernel<<<crd_div_up((long long)B * N * 32, 256), 256, 0, st>>>(dx, pv, dp, ds, B, N, C);
+  crd_launch(attn_out_bwd_ds_kernel, dim3(crd_div_up((long long)B * N * 32, 256)), dim3(256), 0, st, dx, pv, dp, ds, B, N, C);
   CRD_LAUNCH_CHECK();
   cudaMemsetAsync(tmp, 0, (size_t)B * C * 2 * sizeof(float), st);
   ReduceLaunch r = plan_reduce(B, N, C);
-  attn_out_bwd_chan_kernel<<<r.grid, r.block, r.smem, st>>>(dx, s, tmp, B, N, C, r.ppb);
+  crd_launch(attn_out_bwd_chan_kernel, dim3(r.grid), dim3(r.block), r.smem, st, dx, s, tmp, B, N, C, r.ppb);
   CRD_LAUNCH_CHECK();
-  attn_out_bwd_fin_kernel<<<crd_div_up(C, 128), 128, 0, st>>>(tmp, dp, dpv, dbp, B, C);
+  crd_launch(attn_out_bwd_fin_kernel, dim3(crd_div_up(C, 128)), dim3(128), 0, st, tmp, dp, dpv, dbp, B, C);
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -624,7 +640,7 @@ extern "C" int crd_residual_add(const float* x, const void* y, int y_dtype, cons
   CRD_REQUIRE(C % 8 == 0);
   const long long total = (long long)B * N * (C / 8);
   if (total == 0) return 0;
-  CRD_DISPATCH_1(y_dtype, T, residual_add_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(y_dtype, T, crd_launch(residual_add_kernel<T>, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, 
                                  x, (const T*)y, dp, xout, B, N, C));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -634,7 +650,7 @@ extern "C" int crd_scale_cast(const float* dx, const float* dp, void* dy, int dy
   CRD_REQUIRE(C % 8 == 0);
   const long long total = (long long)B * N * (C / 8);
   if (total == 0) return 0;
-  CRD_DISPATCH_1(dy_dtype, T, scale_cast_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dy_dtype, T, crd_launch(scale_cast_kernel<T>, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, 
                                   dx, dp, (T*)dy, B, N, C));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -642,7 +658,7 @@ extern "C" int crd_scale_cast(const float* dx, const float* dp, void* dy, int dy
 extern "C" int crd_add_f32(float* dst, const void* src, int src_dtype, long long n, crd_stream_t stream) {
   CRD_REQUIRE(n % 8 == 0);
   if (n == 0) return 0;
-  CRD_DISPATCH_1(src_dtype, T, add_f32_kernel<T><<<ew_blocks(n / 8), 256, 0, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(src_dtype, T, crd_launch(add_f32_kernel<T>, dim3(ew_blocks(n / 8)), dim3(256), 0, (cudaStream_t)stream, 
                                    dst, (const T*)src, n / 8));
   CRD_LAUNCH_CHECK();
   return 0;

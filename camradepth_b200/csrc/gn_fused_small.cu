@@ -82,6 +82,7 @@ gn_fused_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* _
                     int act, float* __restrict__ ab_out, float* __restrict__ mr_out, float* __restrict__ xbar_out,
                     GfGeom g, int ldx, int ldy, float eps) {
   extern __shared__ float sm[];
+  CRD_PDL_ENTRY();
   cg::cluster_group cluster = cg::this_cluster();
   float* part = sm;                                   // [rows][CT][2]
   float* tot = part + g.rows * g.CT * 2;              // [2][CT] this CTA's pixel range
@@ -188,6 +189,7 @@ gn_fused_bwd_kernel(TD* __restrict__ dy, const TX* __restrict__ x, const float* 
                     const float* __restrict__ addbc, int act, TO* __restrict__ dx, int accumulate, float* dgamma,
                     float* dbeta, GfGeom g, int lddy, int ldx, int lddx) {
   extern __shared__ float sm[];
+  CRD_PDL_ENTRY();
   cg::cluster_group cluster = cg::this_cluster();
   float* part = sm;
   float* tot = part + g.rows * g.CT * 2;              // [2][CT]: sum dz, sum dz*x over this CTA's pixel range
@@ -336,13 +338,15 @@ inline cudaError_t gf_launch(K kernel, const GfGeom& g, size_t smem, cudaStream_
   cfg.blockDim = dim3(GF_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)g.cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = crd_pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 

@@ -58,6 +58,7 @@ __device__ __forceinline__ float st_act_fwd(float z, int act) {
 template <int MODE>
 __global__ void __launch_bounds__(ST_THREADS, 2)
 gn_stream_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CUtensorMap m1, const StParams p) {
+  CRD_PDL_ENTRY();
   constexpr int NIN = (MODE == ST_STATS || MODE == ST_AFFINE) ? 1 : 2;
   constexpr int S = ST_SLOTS / NIN;
   constexpr bool REDUCES = (MODE == ST_STATS || MODE == ST_BWD_REDUCE);
@@ -276,7 +277,7 @@ template <int MODE>
 inline int st_launch(const StLaunch& L, const CUtensorMap& m0, const CUtensorMap& m1, cudaStream_t s) {
   static unsigned long long attr = 0;
   if (int e = ensure_smem_attr(gn_stream_kernel<MODE>, ST_SMEM, attr)) return e;
-  gn_stream_kernel<MODE><<<L.grid, ST_THREADS, ST_SMEM, s>>>(m0, m1, L.p);
+  crd_launch(gn_stream_kernel<MODE>, dim3(L.grid), dim3(ST_THREADS), ST_SMEM, s, m0, m1, L.p);
   return 0;
 }
 

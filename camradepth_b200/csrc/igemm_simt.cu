@@ -62,6 +62,7 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(NT) conv_fwd_kernel(crd_conv_desc d, const TI* __restrict__ x,
                                                       const TI* __restrict__ w, const float* __restrict__ bias,
                                                       TO* __restrict__ y) {
+  CRD_PDL_ENTRY();
   __shared__ __align__(16) float As[2][BK][BM + APAD];
   __shared__ __align__(16) float Bs[2][BK][BN + APAD];
   const int tid = threadIdx.x;
@@ -181,6 +182,7 @@ template <typename TI, typename TD>
 __global__ void __launch_bounds__(NT) conv_wgrad_kernel(crd_conv_desc d, const TI* __restrict__ x,
                                                         const TD* __restrict__ dy, float* __restrict__ dw,
                                                         long long m_per_split) {
+  CRD_PDL_ENTRY();
   __shared__ __align__(16) float Ds[2][BK][BM + APAD];   // [pixel][n]
   __shared__ __align__(16) float Xs[2][BK][BN + APAD];   // [pixel][k]
   const int tid = threadIdx.x;
@@ -284,11 +286,11 @@ extern "C" int crd_conv_fwd(const crd_conv_desc* d, const void* x, const void* w
   dim3 grid(crd_div_up(M, BM), crd_div_up(d->Cout, BN));
   cudaStream_t s = (cudaStream_t)stream;
   if (d->in_dtype == CRD_F32 && d->out_dtype == CRD_F32)
-    conv_fwd_kernel<float, float><<<grid, NT, 0, s>>>(*d, (const float*)x, (const float*)w, bias, (float*)y);
+    crd_launch(conv_fwd_kernel<float, float>, dim3(grid), dim3(NT), 0, s, *d, (const float*)x, (const float*)w, bias, (float*)y);
   else if (d->in_dtype == CRD_BF16 && d->out_dtype == CRD_BF16)
-    conv_fwd_kernel<bf16, bf16><<<grid, NT, 0, s>>>(*d, (const bf16*)x, (const bf16*)w, bias, (bf16*)y);
+    crd_launch(conv_fwd_kernel<bf16, bf16>, dim3(grid), dim3(NT), 0, s, *d, (const bf16*)x, (const bf16*)w, bias, (bf16*)y);
   else if (d->in_dtype == CRD_BF16 && d->out_dtype == CRD_F32)
-    conv_fwd_kernel<bf16, float><<<grid, NT, 0, s>>>(*d, (const bf16*)x, (const bf16*)w, bias, (float*)y);
+    crd_launch(conv_fwd_kernel<bf16, float>, dim3(grid), dim3(NT), 0, s, *d, (const bf16*)x, (const bf16*)w, bias, (float*)y);
   else
     return -2;
   CRD_LAUNCH_CHECK();
@@ -312,11 +314,11 @@ extern "C" int crd_conv_wgrad(const crd_conv_desc* d, const void* x, const void*
   dim3 grid(gx, gy, (unsigned)splits);
   cudaStream_t s = (cudaStream_t)stream;
   if (d->in_dtype == CRD_F32 && d->out_dtype == CRD_F32)
-    conv_wgrad_kernel<float, float><<<grid, NT, 0, s>>>(*d, (const float*)x, (const float*)dy, dw, mps);
+    crd_launch(conv_wgrad_kernel<float, float>, dim3(grid), dim3(NT), 0, s, *d, (const float*)x, (const float*)dy, dw, mps);
   else if (d->in_dtype == CRD_BF16 && d->out_dtype == CRD_BF16)
-    conv_wgrad_kernel<bf16, bf16><<<grid, NT, 0, s>>>(*d, (const bf16*)x, (const bf16*)dy, dw, mps);
+    crd_launch(conv_wgrad_kernel<bf16, bf16>, dim3(grid), dim3(NT), 0, s, *d, (const bf16*)x, (const bf16*)dy, dw, mps);
   else if (d->in_dtype == CRD_BF16 && d->out_dtype == CRD_F32)
-    conv_wgrad_kernel<bf16, float><<<grid, NT, 0, s>>>(*d, (const bf16*)x, (const float*)dy, dw, mps);
+    crd_launch(conv_wgrad_kernel<bf16, float>, dim3(grid), dim3(NT), 0, s, *d, (const bf16*)x, (const float*)dy, dw, mps);
   else
     return -2;
   CRD_LAUNCH_CHECK();

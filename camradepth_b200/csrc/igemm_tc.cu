@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcParams p, const float* __restrict__ bias, void* __restrict__ yv, float* __restrict__ gn) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024-B alignment
   const int TC_STAGES = p.nstages, TC_STAGE_BYTES = p.stage_bytes;
   const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;
@@ -351,6 +352,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();            // everything above (barriers, tensor-map prefetch, TMEM) overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -455,6 +457,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const TcParams p, const float* __restrict__ bias, void* __restrict__ yv, int total_tiles,
                     int ntile_n, float* __restrict__ gn) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int nB = p.nstages;                       // weight ring depth
   const uint32_t b_bytes = (uint32_t)p.bn * 128u;
@@ -485,6 +488,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();            // everything above (barriers, tensor-map prefetch, TMEM) overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -648,6 +652,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                           const TcParams p, const float* __restrict__ bias, void* __restrict__ yv, int total_tiles,
                           int ntile_n, float* __restrict__ gn) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int NS = p.nstages;
   const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
@@ -675,6 +680,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();            // everything above (barriers, tensor-map prefetch, TMEM) overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -871,7 +877,8 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
     const int smem = HL_A_STAGES * HL_A_BYTES + p.nstages * b_bytes + 1024 + 256 + 1024;
     const int total_tiles = p.tiles_w * p.tiles_h * d->B * ntile;
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-    conv_tc_halo_kernel<<<grid, TC_THREADS, smem, s>>>(map_a, map_b, p, bias, y, total_tiles, ntile, gn_sums);
+    if (cudaError_t le = crd_launch(conv_tc_halo_kernel, dim3(grid), dim3(TC_THREADS), smem, s, map_a, map_b, p, bias, y,
+                                    total_tiles, ntile, gn_sums)) return (int)le;
     CRD_LAUNCH_CHECK();
     return 0;
   }
@@ -895,7 +902,8 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
     if (rc) return rc;
     const int total_tiles = crd_div_up(P, TC_BM) * ntile;
     const int grid = total_tiles < pg_sms ? total_tiles : pg_sms;
-    gemm_tc_persistent_kernel<<<grid, TC_THREADS, smem, s>>>(map_a, map_b, p, bias, y, total_tiles, ntile, gn_sums);
+    if (cudaError_t le = crd_launch(gemm_tc_persistent_kernel, dim3(grid), dim3(TC_THREADS), smem, s, map_a, map_b, p, bias,
+                                    y, total_tiles, ntile, gn_sums)) return (int)le;
     CRD_LAUNCH_CHECK();
     return 0;
   }
@@ -923,7 +931,8 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
   cuuint32_t boxb[2] = {TC_BK, (cuuint32_t)p.bn};
   rc = make_map(&map_b, w, 2, dimsb, strb, boxb);
   if (rc) return rc;
-  conv_tc_kernel<<<dim3(gx, ntile), TC_THREADS, smem, s>>>(map_a, map_b, p, bias, y, gn_sums);
+  if (cudaError_t le = crd_launch(conv_tc_kernel, dim3(gx, ntile), dim3(TC_THREADS), smem, s, map_a, map_b, p, bias, y,
+                                  gn_sums)) return (int)le;
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -988,6 +997,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   // with the bias reduction the last 16 KiB of the 200 KiB hold the constant tile of ones (B operand of db)
   const int WG_STAGES = min(WG_MAX_STAGES, ((p.bias ? 183 : 200) * 1024) / WG_STAGE_BYTES);
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + WG_STAGES * WG_STAGE_BYTES;
   const uint32_t bar_full = bars, bar_empty = bars + 8 * WG_MAX_STAGES, bar_tmem = bars + 16 * WG_MAX_STAGES;
@@ -1045,6 +1055,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();            // everything above (barriers, tensor-map prefetch, TMEM) overlapped the previous kernel's tail
 
   if (ntiles > 0) {
     if (warp == 0) {
@@ -1309,9 +1320,11 @@ static int conv_wgrad_tc_impl(const crd_conv_desc* d, const void* x, const void*
   splits = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   const dim3 grid(gy, (unsigned)splits, gz);
   cudaStream_t st = (cudaStream_t)stream;
-  if (WG_PIX == 32) wgrad_tc_kernel<32><<<grid, TC_THREADS, WG_SMEM, st>>>(map_dy, map_x, p, dw, db);
-  else if (WG_PIX == 64) wgrad_tc_kernel<64><<<grid, TC_THREADS, WG_SMEM, st>>>(map_dy, map_x, p, dw, db);
-  else wgrad_tc_kernel<128><<<grid, TC_THREADS, WG_SMEM, st>>>(map_dy, map_x, p, dw, db);
+  cudaError_t le;
+  if (WG_PIX == 32) le = crd_launch(wgrad_tc_kernel<32>, grid, dim3(TC_THREADS), WG_SMEM, st, map_dy, map_x, p, dw, db);
+  else if (WG_PIX == 64) le = crd_launch(wgrad_tc_kernel<64>, grid, dim3(TC_THREADS), WG_SMEM, st, map_dy, map_x, p, dw, db);
+  else le = crd_launch(wgrad_tc_kernel<128>, grid, dim3(TC_THREADS), WG_SMEM, st, map_dy, map_x, p, dw, db);
+  if (le) return (int)le;
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -1348,6 +1361,7 @@ __global__ void __launch_bounds__(TC_THREADS)
 qkmax_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const QkParams p, float* __restrict__ s_out, unsigned short* __restrict__ idx) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)p.bn * 128u;
   const uint32_t stage_bytes = QK_A_BYTES + ((b_bytes + 1023u) & ~1023u);
@@ -1376,6 +1390,7 @@ qkmax_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();            // everything above (barriers, tensor-map prefetch, TMEM) overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1481,7 +1496,8 @@ extern "C" int crd_attn_qkmax_fwd_tc(const void* q, const void* k, float* s, uns
     cuuint32_t box[4] = {64, 1, (cuuint32_t)p.bn, 1};
     if (int e = make_map(&map_k, k, 4, dims, str, box)) return e;
   }
-  qkmax_tc_kernel<<<dim3((N + 127) / 128, B), TC_THREADS, smem, (cudaStream_t)stream>>>(map_q, map_k, p, s, idx);
+  if (cudaError_t le = crd_launch(qkmax_tc_kernel, dim3((N + 127) / 128, B), dim3(TC_THREADS), smem, (cudaStream_t)stream,
+                                  map_q, map_k, p, s, idx)) return (int)le;
   CRD_LAUNCH_CHECK();
   return 0;
 }

@@ -2,7 +2,15 @@
 #include "common.cuh"
 #include "../../include/camradepth_b200.h"
 
+#include <stdlib.h>
+
 unsigned long long g_crd_launches = 0;
+
+bool crd_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("CAMRADEPTH_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
 
 extern "C" int crd_version(void) { return 1; }
 extern "C" unsigned long long crd_launch_count(void) { return g_crd_launches; }

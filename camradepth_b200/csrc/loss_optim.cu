@@ -21,6 +21,7 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 
 __global__ void masked_l1_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target,
                                      float* acc, long long n) {
+  CRD_PDL_ENTRY();
   __shared__ float sh[32];
   float s = 0.f, cnt = 0.f, sq = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -43,6 +44,7 @@ __global__ void masked_l1_fwd_kernel(const float* __restrict__ pred, const float
 __global__ void masked_l1_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target,
                                      const float* __restrict__ acc, const float* __restrict__ gout,
                                      float* __restrict__ dpred, long long n) {
+  CRD_PDL_ENTRY();
   const float scale = gout[0] / acc[1];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -58,6 +60,7 @@ __global__ void masked_l1_bwd_kernel(const float* __restrict__ pred, const float
 
 __global__ void ce_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target, float* acc,
                               int B, int C, long long HW, int ignore_index) {
+  CRD_PDL_ENTRY();
   __shared__ float sh[32];
   float s = 0.f, cnt = 0.f;
   const long long total = (long long)B * HW;
@@ -92,6 +95,7 @@ __device__ __forceinline__ float focal_dce(float ce, float gamma) {
 __global__ void ce_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
                               const float* __restrict__ acc, const float* __restrict__ gout, float gamma,
                               float* __restrict__ dlogits, int B, int C, long long HW, int ignore_index) {
+  CRD_PDL_ENTRY();
   const float ce = acc[0] / acc[1];
   const float coef = gout[0] * (gamma > 0.f ? focal_dce(ce, gamma) : 1.f) / acc[1];
   const long long total = (long long)B * HW;
@@ -119,6 +123,7 @@ __global__ void ce_bwd_kernel(const float* __restrict__ logits, const long long*
 
 __global__ void loss_finalize_kernel(const float* __restrict__ acc, float* __restrict__ out, int kind,
                                      float gamma) {
+  CRD_PDL_ENTRY();
   if (kind == 0) {
     out[0] = acc[0] / acc[1];
     out[1] = sqrtf(acc[2] / acc[1]);
@@ -133,6 +138,7 @@ __global__ void loss_finalize_kernel(const float* __restrict__ acc, float* __res
 // ------------------------------------------------------------------ diffGradNorm
 __global__ void __launch_bounds__(256) mt_sumsq_kernel(const crd_opt_tensor* __restrict__ table,
                                                        const crd_opt_chunk* __restrict__ chunks, float* sumsq) {
+  CRD_PDL_ENTRY();
   __shared__ float sh[32];
   const crd_opt_chunk ck = chunks[blockIdx.x];
   const crd_opt_tensor t = table[ck.tensor];
@@ -152,6 +158,7 @@ __global__ void __launch_bounds__(256) diffgradnorm_kernel(const crd_opt_tensor*
                                                            const float* __restrict__ egn_in, float* egn_out,
                                                            const float* __restrict__ step_size_p, float beta1,
                                                            float beta2, float eps) {
+  CRD_PDL_ENTRY();
   const float step_size = step_size_p[0];
   const crd_opt_chunk ck = chunks[blockIdx.x];
   const crd_opt_tensor t = table[ck.tensor];
@@ -192,6 +199,7 @@ __global__ void __launch_bounds__(256) diffgradnorm_kernel(const crd_opt_tensor*
 // acc[0..3] = (sum sq, sum abs, sum rel, count) within max range; acc[4..7] = same for gt >= thr2.
 __global__ void depth_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt, float* acc,
                                      long long n, float max_depth, float thr1, float thr2) {
+  CRD_PDL_ENTRY();
   __shared__ float sh[32];
   float a[8];
 #pragma unroll
@@ -214,6 +222,7 @@ __global__ void depth_metrics_kernel(const float* __restrict__ pred, const float
 }
 // out[0..2] = RMSE, MAE, REL (max range); out[3..5] = same (second range)
 __global__ void depth_metrics_finalize_kernel(const float* __restrict__ acc, float* __restrict__ out) {
+  CRD_PDL_ENTRY();
   for (int s = 0; s < 2; s++) {
     const float c = acc[4 * s + 3];
     out[3 * s + 0] = sqrtf(acc[4 * s + 0] / c);
@@ -224,6 +233,7 @@ __global__ void depth_metrics_finalize_kernel(const float* __restrict__ acc, flo
 // conf[t][p] += 1 for every pixel with target t != ignore_index and p = argmax_c logits
 __global__ void confusion_kernel(const float* __restrict__ logits, const long long* __restrict__ target, float* conf,
                                  int B, int C, long long HW, int ignore_index) {
+  CRD_PDL_ENTRY();
   const long long total = (long long)B * HW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -241,6 +251,7 @@ __global__ void confusion_kernel(const float* __restrict__ logits, const long lo
 // ------------------------------------------------------------------ input pipeline (dataloader.py:213-245)
 // inverse-normalised lidar GT: g = d > 0 ? (max_depth - min(d, max_depth)) / max_depth : 0
 __global__ void gt_normalize_kernel(const float* __restrict__ d, float* __restrict__ g, long long n, float max_depth) {
+  CRD_PDL_ENTRY();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const float v = fminf(fmaxf(d[i], 0.f), max_depth);
@@ -249,6 +260,7 @@ __global__ void gt_normalize_kernel(const float* __restrict__ d, float* __restri
 }
 // zero-ignoring 3x3 stride-2 pad-1 min-pool (zeros count as "no measurement"; 255 never survives)
 __global__ void minpool_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int Ho, int Wo) {
+  CRD_PDL_ENTRY();
   const long long total = (long long)B * Ho * Wo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -271,6 +283,7 @@ __global__ void minpool_kernel(const float* __restrict__ x, float* __restrict__ 
 // uint8 HWC image -> fp32 channels [c0, c0+3) of an NCHW batch tensor, (v/255 - mean[c]) / std[c]
 __global__ void image_normalize_kernel(const unsigned char* __restrict__ img, float* __restrict__ out, int B, int H,
                                        int W, int Ctot, float m0, float m1, float m2, float s0, float s1, float s2) {
+  CRD_PDL_ENTRY();
   const long long hw = (long long)H * W, total = (long long)B * hw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -289,6 +302,7 @@ __global__ void image_normalize_kernel(const unsigned char* __restrict__ img, fl
 template <typename TS>
 __global__ void seg_resize_kernel(const TS* __restrict__ src, long long* __restrict__ dst, int B, int Hi, int Wi, int Ho,
                                   int Wo) {
+  CRD_PDL_ENTRY();
   const long long total = (long long)B * Ho * Wo;
   const double sh = (double)Hi / (double)Ho, sw = (double)Wi / (double)Wo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -306,6 +320,7 @@ __global__ void seg_resize_kernel(const TS* __restrict__ src, long long* __restr
 __global__ void pack_input_nhwc_kernel(const unsigned char* __restrict__ img, const float* __restrict__ extra,
                                        bf16* __restrict__ dst, int B, int H, int W, int Ce, int ld, float m0, float m1,
                                        float m2, float s0, float s1, float s2) {
+  CRD_PDL_ENTRY();
   const long long hw = (long long)H * W, total = (long long)B * hw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -345,6 +360,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
 // have B*C2 entries (keep = keep_d2).  Single block: thread 0 advances the counter after everyone has read it.
 __global__ void make_masks_kernel(float* __restrict__ out, const float* __restrict__ keep_dp, int n_dp, int B, int n_d2,
                                   int C2, float keep_d2, unsigned long long* __restrict__ state) {
+  CRD_PDL_ENTRY();
   const unsigned long long seed = state[0], step = state[1];
   const long long n_a = (long long)n_dp * B, total = n_a + (long long)n_d2 * B * C2;
   for (long long q = threadIdx.x; q * 4 < total; q += blockDim.x) {
@@ -373,21 +389,21 @@ inline int red_blocks(long long n) {
 extern "C" int crd_masked_l1_fwd(const float* pred, const float* target, float* acc, long long n,
                                  crd_stream_t stream) {
   if (n == 0) return 0;
-  masked_l1_fwd_kernel<<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>(pred, target, acc, n);
+  crd_launch(masked_l1_fwd_kernel, dim3(red_blocks(n)), dim3(256), 0, (cudaStream_t)stream, pred, target, acc, n);
   CRD_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int crd_masked_l1_bwd(const float* pred, const float* target, const float* acc, const float* gout,
                                  float* dpred, long long n, crd_stream_t stream) {
   if (n == 0) return 0;
-  masked_l1_bwd_kernel<<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>(pred, target, acc, gout, dpred, n);
+  crd_launch(masked_l1_bwd_kernel, dim3(red_blocks(n)), dim3(256), 0, (cudaStream_t)stream, pred, target, acc, gout, dpred, n);
   CRD_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int crd_ce_fwd(const float* logits, const long long* target, float* acc, int B, int C, long long HW,
                           int ignore_index, crd_stream_t stream) {
   if ((long long)B * HW == 0) return 0;
-  ce_fwd_kernel<<<red_blocks((long long)B * HW), 256, 0, (cudaStream_t)stream>>>(logits, target, acc, B, C, HW,
+  crd_launch(ce_fwd_kernel, dim3(red_blocks((long long)B * HW)), dim3(256), 0, (cudaStream_t)stream, logits, target, acc, B, C, HW,
                                                                                  ignore_index);
   CRD_LAUNCH_CHECK();
   return 0;
@@ -396,20 +412,20 @@ extern "C" int crd_ce_bwd(const float* logits, const long long* target, const fl
                           float gamma, float* dlogits, int B, int C, long long HW, int ignore_index,
                           crd_stream_t stream) {
   if ((long long)B * HW == 0) return 0;
-  ce_bwd_kernel<<<red_blocks((long long)B * HW), 256, 0, (cudaStream_t)stream>>>(logits, target, acc, gout, gamma,
+  crd_launch(ce_bwd_kernel, dim3(red_blocks((long long)B * HW)), dim3(256), 0, (cudaStream_t)stream, logits, target, acc, gout, gamma,
                                                                                  dlogits, B, C, HW, ignore_index);
   CRD_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int crd_loss_finalize(const float* acc, float* out, int kind, float gamma, crd_stream_t stream) {
-  loss_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(acc, out, kind, gamma);
+  crd_launch(loss_finalize_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, acc, out, kind, gamma);
   CRD_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int crd_mt_sumsq(const crd_opt_tensor* table, const crd_opt_chunk* chunks, int nchunks, float* sumsq,
                             crd_stream_t stream) {
   if (nchunks == 0) return 0;
-  mt_sumsq_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(table, chunks, sumsq);
+  crd_launch(mt_sumsq_kernel, dim3(nchunks), dim3(256), 0, (cudaStream_t)stream, table, chunks, sumsq);
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -418,7 +434,7 @@ extern "C" int crd_diffgradnorm_update(const crd_opt_tensor* table, const crd_op
                                        const float* step_size, float beta1, float beta2, float eps,
                                        crd_stream_t stream) {
   if (nchunks == 0) return 0;
-  diffgradnorm_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(table, chunks, sumsq, egn_in, egn_out, step_size,
+  crd_launch(diffgradnorm_kernel, dim3(nchunks), dim3(256), 0, (cudaStream_t)stream, table, chunks, sumsq, egn_in, egn_out, step_size,
                                                                  beta1, beta2, eps);
   CRD_LAUNCH_CHECK();
   return 0;
@@ -429,23 +445,23 @@ extern "C" int crd_depth_metrics(const float* pred, const float* gt, float* acc,
   if (n == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(acc, 0, 8 * sizeof(float), s);
-  depth_metrics_kernel<<<red_blocks(n), 256, 0, s>>>(pred, gt, acc, n, max_depth, thr1, thr2);
+  crd_launch(depth_metrics_kernel, dim3(red_blocks(n)), dim3(256), 0, s, pred, gt, acc, n, max_depth, thr1, thr2);
   CRD_LAUNCH_CHECK();
-  depth_metrics_finalize_kernel<<<1, 1, 0, s>>>(acc, out);
+  crd_launch(depth_metrics_finalize_kernel, dim3(1), dim3(1), 0, s, acc, out);
   CRD_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int crd_confusion(const float* logits, const long long* target, float* conf, int B, int C, long long HW,
                              int ignore_index, crd_stream_t stream) {
   if ((long long)B * HW == 0) return 0;
-  confusion_kernel<<<red_blocks((long long)B * HW), 256, 0, (cudaStream_t)stream>>>(logits, target, conf, B, C, HW,
+  crd_launch(confusion_kernel, dim3(red_blocks((long long)B * HW)), dim3(256), 0, (cudaStream_t)stream, logits, target, conf, B, C, HW,
                                                                                     ignore_index);
   CRD_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int crd_gt_normalize(const float* d, float* g, long long n, float max_depth, crd_stream_t stream) {
   if (n == 0) return 0;
-  gt_normalize_kernel<<<red_blocks(n), 256, 0, (cudaStream_t)stream>>>(d, g, n, max_depth);
+  crd_launch(gt_normalize_kernel, dim3(red_blocks(n)), dim3(256), 0, (cudaStream_t)stream, d, g, n, max_depth);
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -453,7 +469,7 @@ extern "C" int crd_minpool3x3s2(const float* x, float* y, int B, int H, int W, c
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)B * Ho * Wo;
   if (total == 0) return 0;
-  minpool_kernel<<<red_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, Ho, Wo);
+  crd_launch(minpool_kernel, dim3(red_blocks(total)), dim3(256), 0, (cudaStream_t)stream, x, y, B, H, W, Ho, Wo);
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -462,9 +478,9 @@ extern "C" int crd_seg_resize_nearest(const void* src, int src_is_u8, long long*
   const long long total = (long long)B * Ho * Wo;
   if (total == 0) return 0;
   CRD_REQUIRE(Hi > 0 && Wi > 0);
-  if (src_is_u8) seg_resize_kernel<unsigned char><<<red_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  if (src_is_u8) crd_launch(seg_resize_kernel<unsigned char>, dim3(red_blocks(total)), dim3(256), 0, (cudaStream_t)stream, 
         (const unsigned char*)src, dst, B, Hi, Wi, Ho, Wo);
-  else seg_resize_kernel<long long><<<red_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  else crd_launch(seg_resize_kernel<long long>, dim3(red_blocks(total)), dim3(256), 0, (cudaStream_t)stream, 
         (const long long*)src, dst, B, Hi, Wi, Ho, Wo);
   CRD_LAUNCH_CHECK();
   return 0;
@@ -474,7 +490,7 @@ extern "C" int crd_pack_input_nhwc(const unsigned char* img, const float* extra,
   const long long total = (long long)B * H * W;
   if (total == 0) return 0;
   CRD_REQUIRE(img && dst && ld >= 8 && ld % 8 == 0 && Ce >= 0 && Ce <= 5 && (Ce == 0 || extra));
-  pack_input_nhwc_kernel<<<red_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  crd_launch(pack_input_nhwc_kernel, dim3(red_blocks(total)), dim3(256), 0, (cudaStream_t)stream, 
       img, extra, (bf16*)dst, B, H, W, Ce, ld, mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0], std3_host[1],
       std3_host[2]);
   CRD_LAUNCH_CHECK();
@@ -484,7 +500,7 @@ extern "C" int crd_make_masks(float* out, const float* keep_dp, int n_dp, int B,
                               unsigned long long* state, crd_stream_t stream) {
   CRD_REQUIRE(out && state && (n_dp == 0 || keep_dp) && keep_d2 > 0.f);
   if ((long long)n_dp * B + (long long)n_d2 * B * C2 == 0) return 0;
-  make_masks_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(out, keep_dp, n_dp, B, n_d2, C2, keep_d2, state);
+  crd_launch(make_masks_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, out, keep_dp, n_dp, B, n_d2, C2, keep_d2, state);
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -492,7 +508,7 @@ extern "C" int crd_image_normalize(const unsigned char* img, float* out, int B, 
                                    const float* mean3_host, const float* std3_host, crd_stream_t stream) {
   const long long total = (long long)B * H * W;
   if (total == 0) return 0;
-  image_normalize_kernel<<<red_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  crd_launch(image_normalize_kernel, dim3(red_blocks(total)), dim3(256), 0, (cudaStream_t)stream, 
       img, out, B, H, W, Ctot, mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0], std3_host[1], std3_host[2]);
   CRD_LAUNCH_CHECK();
   return 0;

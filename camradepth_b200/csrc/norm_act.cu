@@ -13,6 +13,7 @@ namespace {
 template <typename T>
 __global__ void chan_stats_kernel(const T* __restrict__ x, float* sums, int B, long long N, int C, int ld,
                                   long long ppb) {
+  CRD_PDL_ENTRY();
   const int c = threadIdx.x * 8, ry = threadIdx.y, rows = blockDim.y, b = blockIdx.y;
   long long p0 = (long long)blockIdx.x * ppb, p1 = p0 + ppb;
   if (p1 > N) p1 = N;
@@ -44,6 +45,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ sums, const float* 
                                    const float* __restrict__ beta, float* __restrict__ ab,
                                    float* __restrict__ mean_rstd, float* __restrict__ xbar, int B, int C, int G,
                                    long long N, float eps) {
+  CRD_PDL_ENTRY();
   extern __shared__ float gs[];             // [G][2]: mean, rstd
   const int b = blockIdx.x;
   const int cpg = C / G;
@@ -96,6 +98,7 @@ template <typename TI, typename TO>
 __global__ void affine_act_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* __restrict__ ab,
                                   const float* __restrict__ post, int act, int B, long long N, int C, int ldx,
                                   int ldy, long long ppb) {
+  CRD_PDL_ENTRY();
   // blockDim = (C/8, rows); each thread keeps the per-(b,c) affine of its 8 channels in registers and
   // streams over the block's pixel range (coalesced 16-byte accesses, no per-pixel parameter loads)
   const int c = threadIdx.x * 8, ry = threadIdx.y, rows = blockDim.y;
@@ -142,6 +145,7 @@ __global__ void gnact_bwd_reduce_kernel(const TD* __restrict__ dy, const TX* __r
                                         const float* __restrict__ ab, const float* __restrict__ post,
                                         const float* __restrict__ addbc, int act, float* pq, TD* dz_out, int B,
                                         long long N, int C, int lddy, int ldx, long long ppb) {
+  CRD_PDL_ENTRY();
   const int c = threadIdx.x * 8, ry = threadIdx.y, rows = blockDim.y, b = blockIdx.y;
   long long p0 = (long long)blockIdx.x * ppb, p1 = p0 + ppb;
   if (p1 > N) p1 = N;
@@ -196,6 +200,7 @@ __global__ void gnact_bwd_reduce_kernel(const TD* __restrict__ dy, const TX* __r
 __global__ void gn_bwd_finalize_kernel(const float* __restrict__ pq, const float* __restrict__ mean_rstd,
                                        const float* __restrict__ gamma, float* __restrict__ coef,
                                        float* dgamma, float* dbeta, int B, int C, int G, long long N) {
+  CRD_PDL_ENTRY();
   extern __shared__ float gs[];             // [G][2]: m1, m2
   const int b = blockIdx.x;
   const int cpg = C / G;
@@ -244,6 +249,7 @@ __global__ void gnact_bwd_apply_kernel(const TD* __restrict__ dy, const TX* __re
                                        const float* __restrict__ addbc, int act, const float* __restrict__ coef,
                                        TO* __restrict__ dx, int accumulate, int B, long long N, int C, int lddy,
                                        int ldx, int lddx, long long ppb) {
+  CRD_PDL_ENTRY();
   const int c = threadIdx.x * 8, ry = threadIdx.y, rows = blockDim.y;
   const int b = blockIdx.y;
   long long p0 = (long long)blockIdx.x * ppb, p1 = p0 + ppb;
@@ -313,7 +319,7 @@ extern "C" int crd_chan_stats(const void* x, int dtype, float* sums, int B, long
     return 0;
   }
   ReduceLaunch r = plan_reduce(B, N, C);
-  CRD_DISPATCH_1(dtype, T, chan_stats_kernel<T><<<r.grid, r.block, r.smem, (cudaStream_t)stream>>>(
+  CRD_DISPATCH_1(dtype, T, crd_launch(chan_stats_kernel<T>, dim3(r.grid), dim3(r.block), r.smem, (cudaStream_t)stream, 
                                 (const T*)x, sums, B, N, C, ld, r.ppb));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -324,7 +330,7 @@ extern "C" int crd_gn_finalize(const float* sums, const float* gamma, const floa
                                crd_stream_t stream) {
   CRD_REQUIRE(G > 0 && C % G == 0);
   if (B == 0) return 0;
-  gn_finalize_kernel<<<B, 256, 2 * G * sizeof(float), (cudaStream_t)stream>>>(sums, gamma, beta, ab, mean_rstd, xbar, B, C, G, N, eps);
+  crd_launch(gn_finalize_kernel, dim3(B), dim3(256), 2 * G * sizeof(float), (cudaStream_t)stream, sums, gamma, beta, ab, mean_rstd, xbar, B, C, G, N, eps);
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -346,7 +352,7 @@ extern "C" int crd_affine_act(const void* x, int in_dtype, void* y, int out_dtyp
     return 0;
   }
   ReduceLaunch r = plan_stream(B, N, C);
-  CRD_DISPATCH_1(in_dtype, TI, CRD_DISPATCH_1(out_dtype, TO, affine_act_kernel<TI, TO><<<r.grid, r.block, 0, s>>>(
+  CRD_DISPATCH_1(in_dtype, TI, CRD_DISPATCH_1(out_dtype, TO, crd_launch(affine_act_kernel<TI, TO>, dim3(r.grid), dim3(r.block), 0, s, 
                                    (const TI*)x, (TO*)y, ab, post, act, B, N, C, ldx, ldy, r.ppb)));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -370,7 +376,7 @@ extern "C" int crd_gnact_bwd_reduce(const void* dy, int dy_dtype, const void* x,
     return 0;
   }
   ReduceLaunch r = plan_reduce(B, N, C);
-  CRD_DISPATCH_1(dy_dtype, TD, CRD_DISPATCH_1(x_dtype, TX, gnact_bwd_reduce_kernel<TD, TX><<<r.grid, r.block, r.smem, s>>>(
+  CRD_DISPATCH_1(dy_dtype, TD, CRD_DISPATCH_1(x_dtype, TX, crd_launch(gnact_bwd_reduce_kernel<TD, TX>, dim3(r.grid), dim3(r.block), r.smem, s, 
                                    (const TD*)dy, (const TX*)x, ab, post, addbc, act, pq, (TD*)dz_out, B, N, C, lddy, ldx, r.ppb)));
   CRD_LAUNCH_CHECK();
   return 0;
@@ -381,7 +387,7 @@ extern "C" int crd_gn_bwd_finalize(const float* pq, const float* mean_rstd, cons
                                    crd_stream_t stream) {
   CRD_REQUIRE(G > 0 && C % G == 0);
   if (B == 0) return 0;
-  gn_bwd_finalize_kernel<<<B, 256, 2 * G * sizeof(float), (cudaStream_t)stream>>>(pq, mean_rstd, gamma, coef, dgamma, dbeta, B, C, G, N);
+  crd_launch(gn_bwd_finalize_kernel, dim3(B), dim3(256), 2 * G * sizeof(float), (cudaStream_t)stream, pq, mean_rstd, gamma, coef, dgamma, dbeta, B, C, G, N);
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -408,7 +414,7 @@ extern "C" int crd_gnact_bwd_apply(const void* dy, int dy_dtype, const void* x, 
   }
   ReduceLaunch r = plan_stream(B, N, C);
   CRD_DISPATCH_1(dy_dtype, TD, CRD_DISPATCH_1(x_dtype, TX, CRD_DISPATCH_1(dx_dtype, TO,
-      gnact_bwd_apply_kernel<TD, TX, TO><<<r.grid, r.block, 0, s>>>((const TD*)dy, (const TX*)x, ab, post, addbc, act,
+      crd_launch(gnact_bwd_apply_kernel<TD, TX, TO>, dim3(r.grid), dim3(r.block), 0, s, (const TD*)dy, (const TX*)x, ab, post, addbc, act,
                                                                    coef, (TO*)dx, accumulate, B, N, C, lddy, ldx,
                                                                    lddx, r.ppb))));
   CRD_LAUNCH_CHECK();

@@ -33,6 +33,7 @@ ab)     # A/B of engine switches: AB="CAMRADEPTH_SPLIT=;CAMRADEPTH_LEAF_STAGES="
         echo "${AB}" | tr ';' '\n' | while read -r kv; do
           echo "== ${kv:-default}" >> gpurun_out/${TAG}_ab.txt
           env ${kv} timeout 600 python bench.py --quick --steps 10 --warmup 3 >> gpurun_out/${TAG}_ab.txt 2>/dev/null
+          [ -n "${AB_LAT}" ] && env ${kv} timeout 300 python tools/bench_latency.py >> gpurun_out/${TAG}_ab.txt 2>/dev/null
         done; cat gpurun_out/${TAG}_ab.txt ;;
 det)    timeout 300 python tools/det_check.py ${DET_VARIANT:-base} > gpurun_out/${TAG}_det_check.txt 2>&1; tail -20 gpurun_out/${TAG}_det_check.txt ;;
 dp2)    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_check.py supervised_seg fp32 > gpurun_out/${TAG}_dp_check.txt 2>&1; tail -4 gpurun_out/${TAG}_dp_check.txt
