@@ -27,7 +27,8 @@ typedef __nv_bfloat16 bf16;
 // pdl_wait() until that kernel has completed and its memory is visible.  Every such kernel calls
 // pdl_launch_dependents() first (lets ITS successor be scheduled early; always safe because the successor waits for
 // full completion) and pdl_wait() before its first global-memory access.  Without the attribute both are no-ops.
-// In a captured CUDA graph the attribute becomes a programmatic dependency edge.  CAMRADEPTH_PDL=0 disables.
+// In a captured CUDA graph the attribute becomes a programmatic dependency edge.  Off unless CAMRADEPTH_PDL=1
+// (measured neutral here, see lib.cu).
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #define CRD_PDL_ENTRY() do { pdl_launch_dependents(); pdl_wait(); } while (0)

@@ -17,6 +17,8 @@ ncu_full) timeout 900 ncu --set full --clock-control none --import-source on -k 
         [ $(stat -c %s gpurun_out/${TAG}_prof_dom.ncu-rep) -gt 25000000 ] && rm -f gpurun_out/${TAG}_prof_dom.ncu-rep ;;
 ncu_stream) timeout 900 ncu --set full --clock-control none -k regex:'gn_stream|dwconv_tma|bicubic_tma|qkmax_tc' -o gpurun_out/${TAG}_prof_ew -f env CONV_ITERS=0 python tools/run_kernels_for_ncu.py > gpurun_out/${TAG}_ncu_ew.log 2>&1
         ncu -i gpurun_out/${TAG}_prof_ew.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_ew_raw.csv 2>/dev/null; rm -f gpurun_out/${TAG}_prof_ew.ncu-rep ;;
+ncu_dw) timeout 600 ncu --set full --clock-control none --import-source on -k regex:'dwconv_tma' -c 2 -o gpurun_out/${TAG}_prof_dw -f env CONV_ITERS=0 python tools/run_kernels_for_ncu.py > gpurun_out/${TAG}_ncu_dw.log 2>&1
+        ncu -i gpurun_out/${TAG}_prof_dw.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_dw_raw.csv 2>/dev/null ;;
 ncu_enc) ENC_STAGES=${ENC_STAGES:-2} timeout 900 ncu --set full --clock-control none --import-source on -k regex:'conv_tc|wgrad_tc|gemm_tc' -o gpurun_out/${TAG}_prof_enc -f python tools/run_encoder_for_ncu.py > gpurun_out/${TAG}_ncu_enc.log 2>&1; tail -3 gpurun_out/${TAG}_ncu_enc.log
         ncu -i gpurun_out/${TAG}_prof_enc.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_enc_raw.csv 2>/dev/null
         [ $(stat -c %s gpurun_out/${TAG}_prof_enc.ncu-rep) -gt 25000000 ] && rm -f gpurun_out/${TAG}_prof_enc.ncu-rep ;;
