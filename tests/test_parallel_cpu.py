@@ -83,3 +83,42 @@ def test_bucketed_allreduce_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _loss_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from camradepth_b200 import losses
+    # per-rank partial sums of a masked-mean loss: [sum of per-pixel losses, valid count, sum of squares]
+    g = torch.Generator().manual_seed(5)
+    per_pixel = [torch.rand(1000, generator=g), 2.0 * torch.rand(300, generator=g)]   # rank 1: fewer valid pixels, larger losses
+    acc = torch.tensor([float(per_pixel[rank].sum()), float(per_pixel[rank].numel()), 0.0])
+    losses.set_data_parallel(world)
+    scale = losses._global_sums(acc)
+    losses.set_data_parallel(1)
+    want = torch.cat(per_pixel)
+    ok = abs(float(acc[0] / acc[1]) - float(want.double().mean())) < 1e-5 and scale == float(world) and float(acc[1]) == 1300.0
+    # gradient convention: every rank back-propagates world * d(global mean)/d(local pixel) = world / global count, so
+    # the all-reduce(AVG) of parameter gradients equals the single-process gradient of the mean over all pixels
+    local_grad = torch.full((1,), scale / float(acc[1]) * per_pixel[rank].numel())  # sum over this rank's pixels
+    dist.all_reduce(local_grad)
+    ok = ok and abs(float(local_grad) / world - 1.0) < 1e-6
+    per_rank_mean_avg = (per_pixel[0].mean() + per_pixel[1].mean()) / 2                # the DDP convention differs:
+    ok = ok and abs(float(per_rank_mean_avg) - float(want.mean())) > 1e-4
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_global_masked_mean_convention_gloo_world2():
+    """losses._global_sums: the loss accumulators of all ranks are summed before the division (reference semantics:
+    one masked mean over the gathered batch, runner.py:193-203), unlike an average of per-rank means."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_loss_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
