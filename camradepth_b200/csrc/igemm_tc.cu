@@ -49,6 +49,9 @@ struct TcParams {
   //   smode 2 (k 3, stride 2, pad 1: patch embeddings 2-4, Cin % 64 == 0): dims {(w%s)*Cin + c, w/s, h%s, h/s, b}
   int smode, cstride;
   int gn_rows;              // smode 1: output rows per sample (tiles run over the merged (b, oh) axis)
+  // Data gradient of a k == stride convolution as a 1x1 GEMM whose read-out is a depth-to-space store: GEMM row =
+  // pixel (b, oh, ow) of dy, GEMM column n = (tap, ci) -> dx[b][oh*s + kh][ow*s + kw][ci]  (windows do not overlap)
+  int d2s, d2s_cin, d2s_ws, d2s_hs;
   int pipe;                 // 1x1 GEMMs: software-pipelined accumulator read-out (CAMRADEPTH_TC_PIPE, default on)
   int gnN;                  // pixels per sample (flat mode: sample of a pixel = pix / gnN) for the GroupNorm sums
   // fused conv + argmax (Seg_Block, utils.py:95-100): am_ncls > 0 -> nothing is written to y; the per-pixel
@@ -282,6 +285,28 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& p, uint32_t taddr,
                                               const float* __restrict__ bias, void* __restrict__ yv,
                                               float* __restrict__ gn, int sb, bool pipe = false) {
   const int ncols = min(p.bn, (p.Cout - n0 + 15) / 16 * 16);      // chunks at or beyond Cout hold nothing
+  if (p.d2s) {
+    // depth-to-space read-out (no bias / statistics): every 16-column chunk lies inside one tap (Cin % 16 == 0)
+    const int s_ = p.d2s;
+    const long long ow = pix % p.d2s_ws, t_ = pix / p.d2s_ws;
+    const long long oh = t_ % p.d2s_hs, b_ = t_ / p.d2s_hs;
+    const long long Wd = (long long)p.d2s_ws * s_;
+    const long long bp = (b_ * p.d2s_hs * s_ + oh * s_) * Wd + ow * s_;
+    TcParams q = p;
+    q.Cout = p.d2s_cin;
+    for (int c = 0; c < ncols; c += 16) {
+      uint32_t r[16];
+      float v[16];
+      tmem_ld16(taddr + (uint32_t)c, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int n = n0 + c, tap = n / p.d2s_cin, ci = n - tap * p.d2s_cin;
+      const int kh = tap / s_, kw = tap - kh * s_;
+#pragma unroll
+      for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]);
+      store_chunk(q, v, ci, ok, bp + kh * Wd + kw, yv);
+    }
+    return;
+  }
   if (!pipe) {
     for (int c = 0; c < ncols; c += 16) {
       uint32_t r[16];
@@ -771,7 +796,13 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
   CRD_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)y & 15) == 0);
   CRD_REQUIRE(d->KH == d->KW);
   int smode = 0;
-  if (d->stride > 1) {
+  const bool d2s = d->stride > 1 && d->transposed;
+  if (d2s) {
+    // data gradient of a k == stride conv: x = dy (B, H, W, Cin = conv output channels), y = dx (B, H*s, W*s, Cout)
+    CRD_REQUIRE(!am && !gn_sums && !bias && d->act == CRD_ACT_NONE && d->KH == d->stride && d->pad == 0);
+    CRD_REQUIRE(d->Ho == d->H * d->stride && d->Wo == d->W * d->stride && d->Cout % 16 == 0 && d->ldy % 16 == 0);
+    CRD_REQUIRE(d->out_dtype == CRD_BF16 && ((uintptr_t)y & 31) == 0 && d->w_tap_stride == 0 && d->w_koff == 0);
+  } else if (d->stride > 1) {
     const int cs = d->stride;
     CRD_REQUIRE(!d->transposed && !am && d->H % cs == 0 && d->W % cs == 0 && d->ldx == d->Cin);
     CRD_REQUIRE(d->Ho == d->H / cs && d->Wo == d->W / cs);
@@ -786,13 +817,18 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
   static unsigned long long attr_v1 = 0;
   if (int e = ensure_smem_attr(conv_tc_kernel, TC_SMEM_BUDGET + 2048, attr_v1)) return e;
   TcParams p;
-  p.flat = (d->KH == 1 && d->stride == 1);
+  p.flat = ((d->KH == 1 && d->stride == 1) || d2s);
   p.smode = smode; p.cstride = d->stride; p.gn_rows = d->Ho;
   p.KH = d->KH; p.KW = d->KW; p.pad = d->pad; p.transposed = d->transposed;
   p.Ho = smode == 1 ? d->B * d->Ho : d->Ho; p.Wo = d->Wo; p.P = P;
   p.Cin = d->Cin; p.Cout = d->Cout;
   p.wstride = d->w_tap_stride ? d->w_tap_stride : d->Cin;
   p.woff = d->w_koff;
+  p.d2s = d2s ? d->stride : 0; p.d2s_cin = d->Cout; p.d2s_ws = d->W; p.d2s_hs = d->H;
+  if (d2s) {                       // GEMM view: [P pixels of dy][K = Cin] x [N = taps * Cout][K]
+    p.KH = p.KW = 1; p.pad = 0; p.transposed = 0;
+    p.Cout = d->KH * d->KW * d->Cout;
+  }
   p.kchunks = (d->Cin + TC_BK - 1) / TC_BK;
   p.ldy = d->ldy; p.out_f32 = d->out_dtype == CRD_F32; p.act = d->act; p.accumulate = d->accumulate;
   p.gnN = d->H * d->W;
@@ -840,7 +876,7 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
     rc = make_map(&map_a, x, 4, dims, str, box);
   }
   if (rc) return rc;
-  const int Ktot = d->KH * d->KW * p.wstride;          // weight row length
+  const int Ktot = p.KH * p.KW * p.wstride;            // weight row length (d2s: the 1x1 GEMM's K = channels of dy)
   cudaStream_t s = (cudaStream_t)stream;
   static int use_halo = -1;
   if (use_halo < 0) {
@@ -850,7 +886,7 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
   // The persistent halo kernel wins whenever one 128-wide N tile covers the output (measured: decoder forward
   // convs 7.9 -> 4.6 ms, depth-head convs 0.8 -> 0.5 ms); the wide-N data gradients of the dense blocks
   // (136..296 output channels, K = 9 * 64..128) stay on the plain kernel (8.6 vs 9.7 ms).
-  if (use_halo && !smode && d->KH == 3 && d->H % 16 == 0 && d->W >= 16 && d->Cout <= 128 && d->Cin >= 32) {
+  if (use_halo && !smode && !d2s && d->KH == 3 && d->H % 16 == 0 && d->W >= 16 && d->Cout <= 128 && d->Cin >= 32) {
     const int num_sms = sm_count();
     static unsigned long long attr_halo = 0;
     if (int e = ensure_smem_attr(conv_tc_halo_kernel, 227 * 1024, attr_halo)) return e;
@@ -888,14 +924,14 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
     static unsigned long long attr_pg = 0;
     if (int e = ensure_smem_attr(gemm_tc_persistent_kernel, 227 * 1024, attr_pg)) return e;
     const int pg_sms = sm_count();
-    const int ntile = (d->Cout + 255) / 256;
-    p.bn = ((d->Cout + ntile - 1) / ntile + 15) / 16 * 16;
+    const int ntile = (p.Cout + 255) / 256;
+    p.bn = ((p.Cout + ntile - 1) / ntile + 15) / 16 * 16;
     p.tmem_cols = p.bn <= 128 ? 256 : 512;               // two accumulator buffers
     p.stage_bytes = TC_A_BYTES + p.bn * TC_BK * 2;
     p.nstages = (200 * 1024) / p.stage_bytes;
     if (p.nstages > TC_MAX_STAGES) p.nstages = TC_MAX_STAGES;
     const int smem = p.nstages * p.stage_bytes + 1024 + 256;
-    cuuint64_t dimsb[2] = {(cuuint64_t)Ktot, (cuuint64_t)d->Cout};
+    cuuint64_t dimsb[2] = {(cuuint64_t)Ktot, (cuuint64_t)p.Cout};
     cuuint64_t strb[1] = {(cuuint64_t)Ktot * 2};
     cuuint32_t boxb[2] = {TC_BK, (cuuint32_t)p.bn};
     rc = make_map(&map_b, w, 2, dimsb, strb, boxb);
@@ -909,24 +945,24 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
   }
   const int gx = p.flat ? crd_div_up(P, TC_BM) : p.tiles_w * p.tiles_h * Bt;
   // N tiles of equal width <= 256 (one pass over A per tile; rows past Cout are zero-filled by TMA)
-  int ntile = (d->Cout + 255) / 256;
+  int ntile = (p.Cout + 255) / 256;
   if (!am) {
     // small problems (fewer CTAs than two per SM) are latency-bound by the serial accumulator read-out of one
     // wide tile: narrower N tiles (>= 32 columns) spread it over the idle SMs; A is re-read from L2, which is
     // free at these sizes
-    const int want = (2 * sm_count() + gx - 1) / gx, most = (d->Cout + 31) / 32;
+    const int want = (2 * sm_count() + gx - 1) / gx, most = (p.Cout + 31) / 32;
     if (want > ntile) ntile = want < most ? want : most;
     if (ntile < 1) ntile = 1;
   }
-  p.bn = ((d->Cout + ntile - 1) / ntile + 15) / 16 * 16;
-  ntile = (d->Cout + p.bn - 1) / p.bn;
+  p.bn = ((p.Cout + ntile - 1) / ntile + 15) / 16 * 16;
+  ntile = (p.Cout + p.bn - 1) / p.bn;
   p.tmem_cols = p.bn <= 32 ? 32 : (p.bn <= 64 ? 64 : (p.bn <= 128 ? 128 : 256));
   p.stage_bytes = TC_A_BYTES + p.bn * TC_BK * 2;
   p.nstages = TC_SMEM_BUDGET / p.stage_bytes;
   if (p.nstages > TC_MAX_STAGES) p.nstages = TC_MAX_STAGES;
   if (p.nstages < 2) p.nstages = 2;
   const int smem = p.nstages * p.stage_bytes + 1024 + 256;
-  cuuint64_t dimsb[2] = {(cuuint64_t)Ktot, (cuuint64_t)d->Cout};
+  cuuint64_t dimsb[2] = {(cuuint64_t)Ktot, (cuuint64_t)p.Cout};
   cuuint64_t strb[1] = {(cuuint64_t)Ktot * 2};
   cuuint32_t boxb[2] = {TC_BK, (cuuint32_t)p.bn};
   rc = make_map(&map_b, w, 2, dimsb, strb, boxb);

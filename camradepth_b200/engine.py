@@ -315,6 +315,16 @@ class Engine:
 
     def conv_dgrad(self, dy, name, dx, accumulate):
         L = self.L[name]
+        if (self._gemm_route(L, dy) and self.strided_igemm and L["k"] == L["stride"] and L["pad"] == 0 and
+                L["cin_p"] == L["cin"] and L["cin"] % 16 == 0 and ops._ld(dx) % 16 == 0 and ops._ld(dy) == L["cout_p"]
+                and dx.shape[1] == dy.shape[1] * L["stride"] and dx.shape[2] == dy.shape[2] * L["stride"]):
+            # k == stride: the windows do not overlap, so the data gradient is a 1x1 GEMM [pixels of dy] x [(tap, ci)]
+            # whose read-out stores each 16-channel chunk at its (oh*s + kh, ow*s + kw) pixel -- no dcol buffer
+            w = self.wpack(name, 2)
+            d = ops.make_desc(dy, dx, L["cout_p"], L["cin_p"], L["k"], L["k"], L["stride"], 0, transposed=1,
+                              accumulate=int(accumulate))
+            ops.conv_fwd(d, dy, w, None, dx, use_tc=True)
+            return
         if self._gemm_route(L, dy):
             w = self.wpack(name, 2)
             K = L["taps"] * L["cin_p"]

@@ -234,3 +234,28 @@ def test_conv_tc_strided_implicit_gemm(case):
     ops.weight_unpack_grad(dwp, gw, None, Cout, Cin, k * k, Cin, False)
     torch.cuda.synchronize()
     assert rel(gw, gw_ref) < 1e-3, rel(gw, gw_ref)
+
+
+@pytest.mark.parametrize("case", [(2, 64, 48, 104, 64, 8), (2, 128, 24, 52, 128, 4), (3, 160, 12, 26, 160, 2), (1, 64, 16, 16, 96, 2)])
+def test_conv_tc_strided_dgrad_depth_to_space(case):
+    """Data gradient of a k == stride conv as a 1x1 GEMM with a depth-to-space read-out (with and without
+    accumulation into an existing gradient), against autograd on the bf16-rounded operands."""
+    from camradepth_b200 import ops
+    B, Cin, H, W, Cout, st = case
+    torch.manual_seed(0)
+    d = dev()
+    x = torch.randn(B, Cin, H, W, device=d)
+    w = torch.randn(Cout, Cin, st, st, device=d) / math.sqrt(Cin * st * st)
+    xr, wr = rnd(x, BF).requires_grad_(True), rnd(w, BF)
+    yr = F.conv2d(xr, wr, None, stride=st)
+    gy = torch.randn_like(yr)
+    (gx_ref,) = torch.autograd.grad(yr, (xr,), rnd(gy, BF))
+    dy = nhwc(gy, BF)
+    w2 = torch.zeros(st * st * Cin, r8(Cout), dtype=BF, device=d)
+    ops.weight_pack(w, w2, None, Cout, Cin, st * st, Cin, r8(Cout), 2)
+    for acc in (0, 1):
+        dx = torch.full((B, H, W, Cin), 1.0 if acc else 7.0, dtype=BF, device=d)
+        desc = ops.make_desc(dy, dx, r8(Cout), Cin, st, st, st, 0, transposed=1, accumulate=acc)
+        ops.conv_fwd(desc, dy, w2, None, dx, use_tc=True)
+        torch.cuda.synchronize()
+        assert rel(nchw(dx, Cin) - (1.0 if acc else 0.0), gx_ref) < (2e-2 if acc else 5e-3)
