@@ -12,7 +12,7 @@ import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(HERE), "include", "camradepth_b200.h")
-LIB_PATH = os.path.join(HERE, "libcamradepth_b200.so")
+LIB_PATH = os.environ.get("CAMRADEPTH_LIB") or os.path.join(HERE, "libcamradepth_b200.so")   # override: A/B of two builds
 
 _SCALARS = {"int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float,
             "unsigned long long": ctypes.c_ulonglong}

@@ -20,7 +20,7 @@ LIB = os.path.join(HERE, "libcamradepth_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-         "-DCRD_BUILD"]
+         "-DCRD_BUILD"] + os.environ.get("CAMRADEPTH_NVCC_EXTRA", "").split()
 
 
 def _sources():

@@ -32,6 +32,10 @@ struct BcParams {
   int TW, strips, rsplit, rows_per_split, nwork;
   int stages, stage_bytes;
   int ntiles, cta_begin[BC_MAX_TILES + 1];      // CTA ranges per 64-channel tile (a short last tile gets fewer)
+  // A last tile of <= 8 channels (the 136-channel decoder tensors: 128 features + depth + padding) would keep 2 of
+  // the 16 channel lanes busy.  It runs "narrow" instead: boxes of 8 channels (16-byte pixels in shared memory),
+  // threads = 2 channel lanes x 112 image columns, its own strip geometry.
+  int narrow, n_TW, n_strips, n_nwork, n_stage_bytes;
   bf16* out;
 };
 
@@ -50,8 +54,9 @@ __device__ __forceinline__ float bc_weight(int o, int s, int n) {
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(BC_THREADS, 2)
-bicubic_tma_kernel(const __grid_constant__ CUtensorMap m_in, const BcParams p) {
+__global__ void __launch_bounds__(BC_THREADS, 3)
+bicubic_tma_kernel(const __grid_constant__ CUtensorMap m_in, const __grid_constant__ CUtensorMap m_nar,
+                   const BcParams p) {
   CRD_PDL_ENTRY();
   constexpr int RH = BWD ? 8 : 5;                // rows per box = register-window depth
   extern __shared__ uint8_t smem_raw[];
@@ -63,33 +68,40 @@ bicubic_tma_kernel(const __grid_constant__ CUtensorMap m_in, const BcParams p) {
   while (tile + 1 < p.ntiles && (int)blockIdx.x >= p.cta_begin[tile + 1]) tile++;
   const int c0 = tile * DW_CH;
   const int first = (int)blockIdx.x - p.cta_begin[tile], step = p.cta_begin[tile + 1] - p.cta_begin[tile];
+  const bool nar = p.narrow && tile == p.ntiles - 1;
+  const int TW = nar ? p.n_TW : p.TW, strips = nar ? p.n_strips : p.strips, nwork = nar ? p.n_nwork : p.nwork;
+  const uint32_t pp = nar ? 16u : 128u;          // bytes per pixel in a shared-memory box row
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, BC_CONSUMERS / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&m_in) : "memory");
+    // (the maps stay kernel parameters: a pointer selected at run time would make the compiler copy them to local memory)
+    if (nar) asm volatile("prefetch.tensormap [%0];" ::"l"(&m_nar) : "memory");
+    else asm volatile("prefetch.tensormap [%0];" ::"l"(&m_in) : "memory");
   }
   __syncthreads();
 
-  const int per_b = p.strips * p.rsplit;
+  const int per_b = strips * p.rsplit;
   if (warp == BC_CONSUMERS / 32) {
     if (lane == 0) {
       int it = 0;
-      for (int i = first; i < p.nwork; i += step) {
+      const uint32_t tx = (uint32_t)(nar ? p.n_stage_bytes : p.stage_bytes);
+      for (int i = first; i < nwork; i += step) {
         const int b = i / per_b, rem = i - b * per_b;
         const int strip = rem / p.rsplit, rs = rem - strip * p.rsplit;
         const int h0 = rs * p.rows_per_split, h1 = min(p.H, h0 + p.rows_per_split);
         const int nrows = BWD ? 2 * (h1 - h0) + 6 : (h1 - h0) + 4;
         const int nb = (nrows + RH - 1) / RH;
-        const int w0 = strip * p.TW;
+        const int w0 = strip * TW;
         for (int k = 0; k < nb; k++, it++) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           const uint32_t bar = bar_full + 8 * s;
-          mbar_expect_tx(bar, (uint32_t)p.stage_bytes);
-          if (BWD) tma_load_4d(base + s * p.stage_bytes, &m_in, bar, c0, 2 * w0 - 3, 2 * h0 - 3 + RH * k, b);
-          else tma_load_4d(base + s * p.stage_bytes, &m_in, bar, c0, w0 - 2, h0 - 2 + RH * k, b);
+          mbar_expect_tx(bar, tx);
+          const int cw = BWD ? 2 * w0 - 3 : w0 - 2, ch = BWD ? 2 * h0 - 3 + RH * k : h0 - 2 + RH * k;
+          if (nar) tma_load_4d(base + s * p.stage_bytes, &m_nar, bar, c0, cw, ch, b);
+          else tma_load_4d(base + s * p.stage_bytes, &m_in, bar, c0, cw, ch, b);
         }
       }
     }
@@ -97,26 +109,26 @@ bicubic_tma_kernel(const __grid_constant__ CUtensorMap m_in, const BcParams p) {
   }
 
   // ------------------------------------------------------------------ consumers
-  const int cg = tid & 15, col = tid >> 4;
+  const int cg = nar ? (tid & 1) : (tid & 15), col = nar ? (tid >> 1) : (tid >> 4);
   const int c = c0 + cg * 4;
-  const bool thr_ok = col < p.TW && c < p.C;
+  const bool thr_ok = col < TW && c < p.C;
   const float k0 = -0.10546875f, k1 = 0.87890625f, k2 = 0.26171875f, k3 = -0.03515625f;   // phase .25 taps
-  const uint32_t row_bytes = (uint32_t)((BWD ? 2 * p.TW + 6 : p.TW + 4) * 128);
+  const uint32_t row_bytes = (uint32_t)(BWD ? 2 * TW + 6 : TW + 4) * pp;
   int it = 0;
-  for (int i = first; i < p.nwork; i += step) {
+  for (int i = first; i < nwork; i += step) {
     const int b = i / per_b, rem = i - b * per_b;
     const int strip = rem / p.rsplit, rs = rem - strip * p.rsplit;
     const int h0 = rs * p.rows_per_split, h1 = min(p.H, h0 + p.rows_per_split);
     const int nrows = BWD ? 2 * (h1 - h0) + 6 : (h1 - h0) + 4;
     const int nb = (nrows + RH - 1) / RH;
-    const int w0 = strip * p.TW, wcol = w0 + col;
+    const int w0 = strip * TW, wcol = w0 + col;
     const bool valid = thr_ok && wcol < p.W;
 
     if (!BWD) {
       // ---------------- forward: input rows h0-2 .. h1+1, five clamped column offsets per thread
       uint32_t coff[5];
 #pragma unroll
-      for (int d = 0; d < 5; d++) coff[d] = (uint32_t)((min(max(wcol + d - 2, 0), p.W - 1) - (w0 - 2)) * 128 + cg * 8);
+      for (int d = 0; d < 5; d++) coff[d] = (uint32_t)(min(max(wcol + d - 2, 0), p.W - 1) - (w0 - 2)) * pp + cg * 8;
       float he[5][4], ho[5][4];
 #pragma unroll
       for (int r = 0; r < 5; r++)
@@ -192,7 +204,7 @@ bicubic_tma_kernel(const __grid_constant__ CUtensorMap m_in, const BcParams p) {
         const uint32_t ph = (it / S) & 1;
         mbar_wait(bar_full + 8 * s, ph);
         if (valid) {
-          const uint32_t ra0 = base + s * p.stage_bytes + (uint32_t)(2 * col * 128 + cg * 8);
+          const uint32_t ra0 = base + s * p.stage_bytes + (uint32_t)(2 * col) * pp + cg * 8;
 #pragma unroll
           for (int r = 0; r < RH; r++) {
             const int ii = RH * k + r;
@@ -201,7 +213,7 @@ bicubic_tma_kernel(const __grid_constant__ CUtensorMap m_in, const BcParams p) {
 #pragma unroll
             for (int t = 0; t < 8; t++) {
               float v[4];
-              lds8_unpack(ra + t * 128, v);
+              lds8_unpack(ra + t * pp, v);
 #pragma unroll
               for (int j = 0; j < 4; j++) acc[j] = fmaf(wx[t], v[j], acc[j]);
             }
@@ -267,11 +279,20 @@ inline int bc_tma_launch(const void* in, BcParams p, cudaStream_t st) {
   p.strips = (p.W + p.TW - 1) / p.TW;
   p.ntiles = (p.C + DW_CH - 1) / DW_CH;
   // CTAs per channel tile: proportional to the tile's work (a short last tile still pays the per-box latency)
-  const int slots = 2 * sm_count();
+  // resident CTAs per SM: 3 with a 72 KB ring each (80 registers), 2 with 104 KB (CAMRADEPTH_BICUBIC_OCC)
+  static int occ = 0;
+  if (!occ) { const char* e = getenv("CAMRADEPTH_BICUBIC_OCC"); occ = (e && e[0] == '2') ? 2 : 3; }
+  const int ring_kb = occ == 3 ? 72 : 104;
+  const int slots = occ * sm_count();
   float wsum = 0.f, wt[BC_MAX_TILES];
+  static int nar_on = -1;
+  if (nar_on < 0) { const char* e = getenv("CAMRADEPTH_BICUBIC_NARROW"); nar_on = (e && e[0] == '0') ? 0 : 1; }
+  const int tail = p.C - (p.ntiles - 1) * DW_CH;
+  p.narrow = (nar_on && p.ntiles > 1 && tail <= 8) ? 1 : 0;
   for (int t = 0; t < p.ntiles; t++) {
     const int valid = p.C - t * DW_CH < DW_CH ? p.C - t * DW_CH : DW_CH;
     wt[t] = valid >= 32 ? 1.f : 0.4f;
+    if (p.narrow && t == p.ntiles - 1) wt[t] = 0.16f;       // 1/8 of a full tile's bytes and thread work
     wsum += wt[t];
   }
   const int per_full = (int)(slots / wsum) > 0 ? (int)(slots / wsum) : 1;
@@ -280,16 +301,24 @@ inline int bc_tma_launch(const void* in, BcParams p, cudaStream_t st) {
   p.rows_per_split = (p.H + p.rsplit - 1) / p.rsplit;
   p.rsplit = (p.H + p.rows_per_split - 1) / p.rows_per_split;
   p.nwork = p.B * p.strips * p.rsplit;
+  const int NAR_COLS = BC_CONSUMERS / 2;
+  p.n_strips = (p.W + NAR_COLS - 1) / NAR_COLS;
+  p.n_TW = (p.W + p.n_strips - 1) / p.n_strips;
+  p.n_strips = (p.W + p.n_TW - 1) / p.n_TW;
+  p.n_nwork = p.B * p.n_strips * p.rsplit;
   p.cta_begin[0] = 0;
   for (int t = 0; t < p.ntiles; t++) {
     int n = (int)(slots * wt[t] / wsum);
+    const int nw = (p.narrow && t == p.ntiles - 1) ? p.n_nwork : p.nwork;
     if (n < 1) n = 1;
-    if (n > p.nwork) n = p.nwork;
+    if (n > nw) n = nw;
     p.cta_begin[t + 1] = p.cta_begin[t] + n;
   }
   const int RH = BWD ? 8 : 5;
   p.stage_bytes = (wmul * p.TW + halo) * RH * 128;
-  p.stages = (104 * 1024) / p.stage_bytes;
+  p.n_stage_bytes = (wmul * p.n_TW + halo) * RH * 16;
+  if (p.narrow && p.n_stage_bytes > p.stage_bytes) p.stage_bytes = (p.n_stage_bytes + 127) / 128 * 128;
+  p.stages = (ring_kb * 1024) / p.stage_bytes;
   if (p.stages > BC_MAX_STAGES) p.stages = BC_MAX_STAGES;
   if (p.stages < 2) return -21;
   const int smem = p.stages * p.stage_bytes + 16 * BC_MAX_STAGES + 256;
@@ -301,7 +330,12 @@ inline int bc_tma_launch(const void* in, BcParams p, cudaStream_t st) {
   cuuint64_t str[3] = {(cuuint64_t)p.ld_in * 2, (cuuint64_t)Wi * p.ld_in * 2, (cuuint64_t)Hi * Wi * p.ld_in * 2};
   cuuint32_t box[4] = {DW_CH, (cuuint32_t)(wmul * p.TW + halo), (cuuint32_t)RH, 1};
   if (int e = make_map(&m_in, in, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
-  crd_launch(bicubic_tma_kernel<BWD>, dim3(p.cta_begin[p.ntiles]), dim3(BC_THREADS), smem, st, m_in, p);
+  CUtensorMap m_nar = m_in;
+  if (p.narrow) {
+    cuuint32_t boxn[4] = {8, (cuuint32_t)(wmul * p.n_TW + halo), (cuuint32_t)RH, 1};
+    if (int e = make_map(&m_nar, in, 4, dims, str, boxn, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+  }
+  crd_launch(bicubic_tma_kernel<BWD>, dim3(p.cta_begin[p.ntiles]), dim3(BC_THREADS), smem, st, m_in, m_nar, p);
   return 0;
 }
 

@@ -1005,6 +1005,12 @@ struct WgParams {
   int Cin, Cout, kchunks;
   int mblocks;              // 64-channel blocks of dY in this launch (1 or 2)
   int halo;                 // 3x3: one X box with TH+2 rows per (chunk, kw); the kh taps are its 2-KiB row offsets
+  // halo mode with Cout <= 64: a single dY block would leave rows 64..127 of the M = 128 MMA idle.  They take a
+  // second dY box shifted DOWN one image row instead, and the MMA runs over the kh = 1, 2 row views of X only
+  // (N = 128): rows 0..63 then hold taps kh = 1, 2 and rows 64..127 tap kh = 0 (plus a discarded copy of kh = 1):
+  //   sum_px dY[oh+1] X[oh + j - 1] = sum_px' dY[oh'] X[oh' + (j - 1) - 1],  the missing px' row 0 meets only padding.
+  // Three taps in one 128x128 MMA instead of one 128x192 whose upper half is garbage.
+  int dual;
   int cpc;                  // 1x1: 64-channel chunks of X per CTA (3, or fewer when the launch would not fill the GPU)
   int bias;                 // 1x1 only: also produce db[co] = sum_px dY (an extra N=64 MMA against a tile of ones)
   int smode, cstride, kwg;  // strided convs through the 5-D X maps of the forward kernel; kwg = groups of <= 3 kw taps
@@ -1096,7 +1102,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   if (ntiles > 0) {
     if (warp == 0) {
       if (lane == 0) {
-        const uint32_t tx = p.halo ? (uint32_t)mblocks * WG_BLK_BYTES + WG_HALO_X_BYTES
+        const uint32_t tx = p.halo ? (uint32_t)(p.dual ? 2 : mblocks) * WG_BLK_BYTES + WG_HALO_X_BYTES
                                    : (uint32_t)(mblocks + nblk) * WG_BLK_BYTES;
         // tile coordinates advance incrementally (no 64-bit divisions on the producer's critical path)
         int tw = 0, th = 0, bb = 0, m0 = 0;
@@ -1121,8 +1127,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             m0 += WG_PIX;
           } else {
             const int oh0 = th * p.TH, ow0 = tw * p.TW;
-            for (int j = 0; j < mblocks; j++)
-              tma_load_4d(sa + j * WG_BLK_BYTES, &map_dy, bar, co0 + 64 * j, ow0, oh0, bb);
+            if (p.dual) {
+              tma_load_4d(sa, &map_dy, bar, co0, ow0, oh0, bb);
+              tma_load_4d(sa + WG_BLK_BYTES, &map_dy, bar, co0, ow0, oh0 + 1, bb);
+            } else {
+              for (int j = 0; j < mblocks; j++)
+                tma_load_4d(sa + j * WG_BLK_BYTES, &map_dy, bar, co0 + 64 * j, ow0, oh0, bb);
+            }
             if (p.smode == 1) {
               for (int j = 0; j < nblk; j++)
                 tma_load_5d(sb + j * WG_BLK_BYTES, &map_x, bar, c0, kw0 + j, ow0, kh, oh0);
@@ -1149,7 +1160,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     } else if (warp == 1) {
       if (lane == 0) {
         // M = 128 (rows beyond the loaded dY blocks hold stale smem and are ignored by the epilogue)
-        const uint32_t idesc = umma_idesc_bf16(128, nblk * 64) | (1u << 15) | (1u << 16);   // A, B MN-major
+        const uint32_t idesc = umma_idesc_bf16(128, p.dual ? 128 : nblk * 64) | (1u << 15) | (1u << 16);   // A, B MN-major
+        const uint32_t b_first = p.dual ? 2048u : 0u;          // dual: the N blocks start at the kh = 1 row view
         const uint32_t idesc1 = umma_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);
         for (int it = 0; it < ntiles; it++) {
           const int s = it % WG_STAGES;
@@ -1161,7 +1173,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
           for (int k = 0; k < WG_PIX / 16; k++) {       // 16 pixels (two 8-row groups = 2048 B) per MMA
             const uint64_t ad = umma_desc_mnmajor_sw128(sa + k * 2048, WG_BLK_BYTES);
             // halo mode: N block j = tap kh=j = the same box shifted by j image rows (16 px * 128 B = 2 KiB)
-            const uint64_t bd = umma_desc_mnmajor_sw128(sb + k * 2048, p.halo ? 2048u : (uint32_t)WG_BLK_BYTES);
+            const uint64_t bd = umma_desc_mnmajor_sw128(sb + b_first + k * 2048,
+                                                        p.halo ? 2048u : (uint32_t)WG_BLK_BYTES);
             umma_bf16_ss(tmem_base, ad, bd, idesc, (it | k) != 0);
             if (do_bias)          // columns 192..255: every column = sum over the pixels of dY
               umma_bf16_ss(tmem_base + 192, ad, umma_desc_mnmajor_sw128(ones + k * 2048, WG_BLK_BYTES), idesc1,
@@ -1173,15 +1186,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       }
     } else {
       const int lg = warp & 3;
-      const int co = co0 + lg * 32 + lane;
+      const int mrow = lg * 32 + lane;
+      const int co = co0 + (p.dual ? (mrow & 63) : mrow);
       mbar_wait(bar_tmem, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int c = 0; c < nblk * 64; c += 16) {
+      // dual: rows 64..127 contribute only their first N block (tap kh = 0); warps 2, 3 stop after 64 columns
+      const int ncols = p.dual ? (lg >= 2 ? 64 : 128) : nblk * 64;
+      for (int c = 0; c < ncols; c += 16) {
         uint32_t r[16];
         tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (co >= p.Cout || lg * 32 + lane >= mblocks * 64) continue;
-        const int j = c >> 6, col = c & 63;
+        if (co >= p.Cout || (!p.dual && mrow >= mblocks * 64)) continue;
+        const int j = p.dual ? (lg >= 2 ? 0 : (c >> 6) + 1) : (c >> 6), col = c & 63;
         long long kbase;
         int cc;
         if (p.KH > 1) {
@@ -1268,6 +1284,9 @@ static int conv_wgrad_tc_impl(const crd_conv_desc* d, const void* x, const void*
   if (wg_halo < 0) { const char* e = getenv("CAMRADEPTH_WG_HALO"); wg_halo = (e && e[0] == '0') ? 0 : 1; }
   p.halo = (wg_halo && !smode && d->KH == 3 && d->W >= 16) ? 1 : 0;
   p.bias = db != nullptr;
+  static int wg_dual = -1;
+  if (wg_dual < 0) { const char* e = getenv("CAMRADEPTH_WG_DUAL"); wg_dual = (e && e[0] == '0') ? 0 : 1; }
+  p.dual = (wg_dual && p.halo && p.mblocks == 1 && !p.bias) ? 1 : 0;
   // pixel tiles run over the OUTPUT image (smode 1: one image of B*Ho rows, the (b, oh) axis of the 5-D X map)
   const int Wt = smode ? d->Wo : d->W, Ht = smode == 1 ? d->B * d->Ho : (smode == 2 ? d->Ho : d->H);
   const int Bt = smode == 1 ? 1 : d->B;

@@ -13,6 +13,8 @@ scalar is refreshed from `group['lr']` (so LR schedulers keep working) -- and st
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -150,6 +152,9 @@ class GraphedDataParallelStep(GraphedTrainStep):
         if global_loss_mean is None:
             global_loss_mean = getattr(model, "global_loss_mean", True)
         self.global_mean = bool(global_loss_mean) and self.world > 1
+        # experiment switches (tools/dp_overhead.py): "noloss" / "nobucket" skip the respective exchange (results are
+        # then per-rank, for timing only), "onegraph" additionally captures the whole step into one graph
+        self._debug = set(filter(None, os.environ.get("CAMRADEPTH_DP_DEBUG", "").split(",")))
         self.ui = float(update_interval)
         self.static = {k: v.clone() for k, v in example_batch.items()}
         m = self.model
@@ -174,7 +179,7 @@ class GraphedDataParallelStep(GraphedTrainStep):
         torch.cuda.synchronize()
         self._ranges = {t: bucket_ranges(eng.names, eng.pg_offsets, t) for t in self.TAGS}
         # ---- capture
-        if self.world == 1:
+        if self.world == 1 or "onegraph" in self._debug:
             segments = [["fwd", "loss"] + list(self.TAGS[1:]) + ["opt"]]
         else:
             segments = [["fwd"], ["loss"]] + [[t] for t in self.TAGS[1:]] + [["opt"]]
@@ -248,10 +253,12 @@ class GraphedDataParallelStep(GraphedTrainStep):
                 p.grad = self.flat[o:o + sz].view(p.shape)
 
     def _allreduce_losses(self):
-        if self.global_mean:
+        if self.global_mean and "noloss" not in self._debug:
             self._dist.all_reduce(self.lacc, op=self._dist.ReduceOp.SUM, group=self.group)
 
     def _allreduce_bucket(self, tag, works):
+        if "nobucket" in self._debug:
+            return
         for (a, c) in self._ranges[tag]:
             t = self.flat[a:c]
             if self._dist.get_backend(self.group) == "nccl":

@@ -40,6 +40,14 @@ ab)     # A/B of engine switches: AB="CAMRADEPTH_SPLIT=;CAMRADEPTH_LEAF_STAGES="
 det)    timeout 300 python tools/det_check.py ${DET_VARIANT:-base} > gpurun_out/${TAG}_det_check.txt 2>&1; tail -20 gpurun_out/${TAG}_det_check.txt ;;
 dp2)    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_check.py supervised_seg fp32 > gpurun_out/${TAG}_dp_check.txt 2>&1; tail -4 gpurun_out/${TAG}_dp_check.txt
         timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/dp_check.py base bf16 >> gpurun_out/${TAG}_dp_check.txt 2>&1; tail -3 gpurun_out/${TAG}_dp_check.txt ;;
+ablib)  # same-box A/B of library builds: ABLIBS="ab_libs/lib_head.so ab_libs/lib_lane0.so default"
+        for L in ${ABLIBS}; do
+          echo "==== ${L}" >> gpurun_out/${TAG}_ablib.txt
+          if [ "$L" = default ]; then unset CAMRADEPTH_LIB; else export CAMRADEPTH_LIB=$PWD/$L; fi
+          timeout 300 python tools/profile_convs.py 32 2>&1 | grep "depth_upsample.4\|conv launches total" >> gpurun_out/${TAG}_ablib.txt
+          timeout 600 python bench.py --quick --steps 10 --warmup 3 2>/dev/null | cut -c1-200 >> gpurun_out/${TAG}_ablib.txt
+        done; unset CAMRADEPTH_LIB; cat gpurun_out/${TAG}_ablib.txt ;;
+dpo)    N=${NGPU:-2}; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 tools/dp_overhead.py 30 > gpurun_out/${TAG}_dp_overhead_${N}gpu.txt 2>&1; grep "ms/step" gpurun_out/${TAG}_dp_overhead_${N}gpu.txt || tail -20 gpurun_out/${TAG}_dp_overhead_${N}gpu.txt ;;
 benchN) N=${NGPU:-2}; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N > gpurun_out/${TAG}_bench_${N}gpu.json 2> gpurun_out/${TAG}_bench_${N}gpu.err; tail -c 1500 gpurun_out/${TAG}_bench_${N}gpu.json; tail -5 gpurun_out/${TAG}_bench_${N}gpu.err ;;
 esac
 done
