@@ -52,10 +52,8 @@ __device__ __forceinline__ void stg8_bf16(bf16* p, const float (&v)[4]) {
   *reinterpret_cast<uint2*>(p) = r;
 }
 
-// HI: one more resident CTA per SM (forward 3 instead of 2, backward 2 instead of 1) at the price of a register cap
-// with a few spills and a shorter ring; chosen per direction by measurement (CAMRADEPTH_DWCONV_OCC)
-template <bool BWD, bool HI>
-__global__ void __launch_bounds__(DW_THREADS, (BWD ? 1 : 2) + (HI ? 1 : 0))
+template <bool BWD>
+__global__ void __launch_bounds__(DW_THREADS, BWD ? 1 : 2)
 dwconv_tma_kernel(const __grid_constant__ CUtensorMap m_a, const __grid_constant__ CUtensorMap m_x, const DwParams p) {
   CRD_PDL_ENTRY();
   extern __shared__ uint8_t smem_raw[];
@@ -250,8 +248,8 @@ inline bool dw_tma_eligible(int dtype, int B, int H, int W, int C, const void* p
   return true;
 }
 
-template <bool BWD, bool HI>
-inline int dw_tma_launch_occ(const void* a_in, const void* x_in, DwParams p, cudaStream_t st) {
+template <bool BWD>
+inline int dw_tma_launch(const void* a_in, const void* x_in, DwParams p, cudaStream_t st) {
   // strip width: fewest loaded columns (strips * (TW + 2)); ties -> wider strips
   int best = DW_COLS; long long best_cost = -1;
   for (int tw = DW_COLS; tw >= 8; tw--) {
@@ -261,8 +259,7 @@ inline int dw_tma_launch_occ(const void* a_in, const void* x_in, DwParams p, cud
   p.TW = best;
   p.strips = (p.W + p.TW - 1) / p.TW;
   const int ctiles = p.C / DW_CH;
-  const int occ = (BWD ? 1 : 2) + (HI ? 1 : 0);
-  const int slots = occ * sm_count();
+  const int slots = (BWD ? 1 : 2) * sm_count();
   int per_tile = slots / ctiles;
   if (per_tile < 1) per_tile = 1;
   // split rows so that every CTA gets several work items (load balance) while row ranges stay >= 6 rows
@@ -274,13 +271,13 @@ inline int dw_tma_launch_occ(const void* a_in, const void* x_in, DwParams p, cud
   if (per_tile > p.nwork) per_tile = p.nwork;
   p.a_bytes = (p.TW + 2) * DW_RH * 128;
   p.stage_bytes = p.a_bytes + (BWD ? p.TW * DW_RH * 128 : 0);
-  const int budget = (BWD ? (HI ? 100 : 200) : (HI ? 70 : 106)) * 1024;
+  const int budget = BWD ? 200 * 1024 : 106 * 1024;
   p.stages = budget / p.stage_bytes;
   if (p.stages > DW_MAX_STAGES) p.stages = DW_MAX_STAGES;
   if (BWD && p.stages * p.stage_bytes < 10 * DW_COLS * DW_CH * 4) return -20;   // reduction scratch must fit the ring
   const int smem = p.stages * p.stage_bytes + 16 * DW_MAX_STAGES + 256;
   static unsigned long long attr = 0;
-  if (int e = ensure_smem_attr(dwconv_tma_kernel<BWD, HI>, 200 * 1024 + 16 * DW_MAX_STAGES + 256, attr)) return e;
+  if (int e = ensure_smem_attr(dwconv_tma_kernel<BWD>, 200 * 1024 + 16 * DW_MAX_STAGES + 256, attr)) return e;
   CUtensorMap m_a, m_x;
   cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
   cuuint64_t str[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.W * p.C * 2, (cuuint64_t)p.H * p.W * p.C * 2};
@@ -291,21 +288,8 @@ inline int dw_tma_launch_occ(const void* a_in, const void* x_in, DwParams p, cud
     cuuint32_t box_x[4] = {DW_CH, (cuuint32_t)p.TW, DW_RH, 1};
     if (int e = make_map(&m_x, x_in, 4, dims, str, box_x, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
   }
-  crd_launch(dwconv_tma_kernel<BWD, HI>, dim3(dim3(per_tile, ctiles)), dim3(DW_THREADS), smem, st, m_a, m_x, p);
+  crd_launch(dwconv_tma_kernel<BWD>, dim3(dim3(per_tile, ctiles)), dim3(DW_THREADS), smem, st, m_a, m_x, p);
   return 0;
-}
-template <bool BWD>
-inline int dw_tma_launch(const void* a_in, const void* x_in, DwParams p, cudaStream_t st) {
-  // CAMRADEPTH_DWCONV_OCC: two characters, forward then backward, '1' = one more resident CTA per SM
-  static int hi = -1;
-  if (hi < 0) {
-    const char* e = getenv("CAMRADEPTH_DWCONV_OCC");
-    hi = 0;
-    if (e && e[0] == '1') hi |= 1;
-    if (e && e[0] && e[1] == '1') hi |= 2;
-  }
-  if (hi & (BWD ? 2 : 1)) return dw_tma_launch_occ<BWD, true>(a_in, x_in, p, st);
-  return dw_tma_launch_occ<BWD, false>(a_in, x_in, p, st);
 }
 
 }  // namespace
