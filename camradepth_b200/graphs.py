@@ -125,12 +125,14 @@ class GraphedDataParallelStep(GraphedTrainStep):
 
         graph 0   forward + per-rank loss sums
         (NCCL)    all-reduce of the 11 loss accumulators -> global masked means (SURVEY.md §8e caveat 1)
-        graph 1   loss finalize + loss gradients + backward of the heads and the decoder pyramid
-        (NCCL)    all-reduce(AVG) of the decoder bucket of the flat gradient buffer, on NCCL's stream,
-        graph 2   backward of encoder stage 4      ... overlapped with this graph, and so on for
-        graph 3-5 backward of stages 3, 2, 1       the stage buckets (runner.py:135-136 replacement)
-        graph 6   diffGradNorm step (waits for the last bucket)
+        graph 1   loss finalize + loss gradients + backward of the heads, the decoder pyramid and encoder stages 4..2
+        (NCCL)    all-reduce(AVG) of those buckets of the flat gradient buffer (81 of 88 MB), on NCCL's stream,
+        graph 2   backward of encoder stage 1 and the first patch embedding      ... overlapped with this graph
+        (NCCL)    all-reduce of the last bucket (runner.py:135-136 replacement)
+        graph 3   diffGradNorm step (waits for the buckets)
 
+    The cut points are the gradient-bucket boundaries of the backward program (`CAMRADEPTH_DP_CUTS`, default one cut
+    after stage 2: every additional graph boundary costs ~0.1 ms, see profiles/r2_dp_overhead_2gpu.txt).
     With one process (world == 1) all phases are captured into ONE graph.  The public surface is the one of
     `GraphedTrainStep`: `__call__(batch)`, `prefetch(host_batch)`, `run_prefetched()`; the loss returned is the
     global (whole data-parallel batch) loss.  `model` may be a `parallel.DataParallel` wrapper or the bare module.
@@ -182,7 +184,19 @@ class GraphedDataParallelStep(GraphedTrainStep):
         if self.world == 1 or "onegraph" in self._debug:
             segments = [["fwd", "loss"] + list(self.TAGS[1:]) + ["opt"]]
         else:
-            segments = [["fwd"], ["loss"]] + [[t] for t in self.TAGS[1:]] + [["opt"]]
+            # cut points of the backward program (tags after which a new graph starts).  Every graph boundary costs
+            # ~0.1 ms (profiles/r2_dp_overhead_2gpu.txt), every bucket left to the last graph is exposed: one cut
+            # after encoder stage 2 sends 81 of the 88 MB while the stage-1 backward (~4 ms) still runs.
+            cuts = set(filter(None, os.environ.get("CAMRADEPTH_DP_CUTS", "stage1").split(",")))
+            segments, cur = [["fwd"]], ["loss"]
+            for t in self.TAGS[1:]:
+                cur.append(t)
+                if t in cuts:
+                    segments.append(cur)
+                    cur = []
+            if cur:
+                segments.append(cur)
+            segments.append(["opt"])
         pool = torch.cuda.graph_pool_handle()
         self.graphs = []
         for seg in segments:
@@ -299,12 +313,13 @@ class GraphedDataParallelStep(GraphedTrainStep):
                 self._wait(works)
             g.replay()
             if self.world > 1:
-                if seg[0] == "fwd":
-                    self._allreduce_losses()
-                elif seg[0] == "loss":
-                    self._allreduce_bucket("decoder", works)
-                elif seg[0] in self.TAGS:
-                    self._allreduce_bucket(seg[0], works)
+                for ph in seg:                       # exchanges of everything this graph completed
+                    if ph == "fwd":
+                        self._allreduce_losses()
+                    elif ph == "loss":
+                        self._allreduce_bucket("decoder", works)
+                    elif ph in self.TAGS:
+                        self._allreduce_bucket(ph, works)
         if self.scheduler is not None:
             self.scheduler.step()
         return self.loss

@@ -35,7 +35,11 @@ def main():
     batch = {k: v.to(dev) for k, v in make_batch(32, 192, 416, seed=rank, input_channels=C.args.input_channels).items()}
     variants = [("onegraph", "onegraph,noloss,nobucket"), ("graphs", "noloss,nobucket"), ("buckets", "noloss"),
                 ("full", ""), ("onegraph", "onegraph,noloss,nobucket"), ("full", "")]
+    if os.environ.get("DPO_CUTS"):      # e.g. DPO_CUTS="stage3,stage2,stage1,stage0;stage1;stage2;": one full run per setting
+        variants = [("cuts=" + c, c) for c in os.environ["DPO_CUTS"].split(";")] * 2
     for name, dbg in variants:
+        if name.startswith("cuts="):
+            os.environ["CAMRADEPTH_DP_CUTS"], dbg = dbg, ""
         os.environ["CAMRADEPTH_DP_DEBUG"] = dbg
         opt = C.diffGradNorm(model.parameters(), lr=1e-4)
         g = GraphedDataParallelStep(net, opt, batch)
