@@ -333,7 +333,10 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& p, uint32_t taddr,
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+// MINB = 3: 96 registers (12 bytes of spill) for short-K launches whose ring is small enough for three CTAs per SM;
+// MINB = 2: 149 registers for everything else (the wide read-outs lose 15-25 % under the 96-register cap)
+template <int MINB>
+__global__ void __launch_bounds__(TC_THREADS, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcParams p, const float* __restrict__ bias, void* __restrict__ yv, float* __restrict__ gn) {
   extern __shared__ uint8_t smem_raw[];
@@ -815,7 +818,9 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
   const long long P = (long long)d->B * d->H * d->W;
   if (P == 0) return 0;
   static unsigned long long attr_v1 = 0;
-  if (int e = ensure_smem_attr(conv_tc_kernel, TC_SMEM_BUDGET + 2048, attr_v1)) return e;
+  if (int e = ensure_smem_attr(conv_tc_kernel<2>, TC_SMEM_BUDGET + 2048, attr_v1)) return e;
+  static unsigned long long attr_v3 = 0;
+  if (int e = ensure_smem_attr(conv_tc_kernel<3>, TC_SMEM_BUDGET + 2048, attr_v3)) return e;
   TcParams p;
   p.flat = ((d->KH == 1 && d->stride == 1) || d2s);
   p.smode = smode; p.cstride = d->stride; p.gn_rows = d->Ho;
@@ -946,12 +951,31 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
   const int gx = p.flat ? crd_div_up(P, TC_BM) : p.tiles_w * p.tiles_h * Bt;
   // N tiles of equal width <= 256 (one pass over A per tile; rows past Cout are zero-filled by TMA)
   int ntile = (p.Cout + 255) / 256;
+  const int nk_total = p.KH * p.KW * p.kchunks;         // pipeline iterations of one CTA
+  static int occ3 = -1;
+  if (occ3 < 0) { const char* e = getenv("CAMRADEPTH_TC_OCC3"); occ3 = (e && e[0] == '0') ? 0 : 1; }
   if (!am) {
-    // small problems (fewer CTAs than two per SM) are latency-bound by the serial accumulator read-out of one
-    // wide tile: narrower N tiles (>= 32 columns) spread it over the idle SMs; A is re-read from L2, which is
-    // free at these sizes
-    const int want = (2 * sm_count() + gx - 1) / gx, most = (p.Cout + 31) / 32;
-    if (want > ntile) ntile = want < most ? want : most;
+    // small problems (fewer CTAs than the GPU holds at once) are latency-bound by the serial accumulator read-out of
+    // one wide tile: narrower N tiles (>= 32 columns) spread it over the idle SMs; A is re-read from L2, which is
+    // free at these sizes.  The launch should stay ONE wave: 78 x 4 = 312 CTAs on 296 slots ran 16 CTAs in a second
+    // wave (stage-3 GEMMs), 312 x 1 likewise (stage-2, N = 128).  Short-K launches (ring <= 3 stages, N tile <= 128:
+    // smem and TMEM for three CTAs per SM) count 3 slots per SM.
+    const int most = (p.Cout + 31) / 32;
+    if (occ3) {
+      const int slots3 = 3 * sm_count(), slots2 = 2 * sm_count();
+      int best = ntile;
+      for (int nt = ntile; nt <= most; nt++) {
+        const int bn = ((p.Cout + nt - 1) / nt + 15) / 16 * 16;
+        const int real = (p.Cout + bn - 1) / bn;
+        const int st = nk_total < TC_MAX_STAGES ? nk_total : TC_MAX_STAGES;
+        const bool three = bn <= 128 && (long long)st * (TC_A_BYTES + bn * TC_BK * 2) + 2048 <= 72 * 1024;
+        if ((long long)gx * real <= (three ? slots3 : slots2)) best = nt;
+      }
+      ntile = best;
+    } else {
+      const int want = (2 * sm_count() + gx - 1) / gx;
+      if (want > ntile) ntile = want < most ? want : most;
+    }
     if (ntile < 1) ntile = 1;
   }
   p.bn = ((p.Cout + ntile - 1) / ntile + 15) / 16 * 16;
@@ -960,6 +984,7 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
   p.stage_bytes = TC_A_BYTES + p.bn * TC_BK * 2;
   p.nstages = TC_SMEM_BUDGET / p.stage_bytes;
   if (p.nstages > TC_MAX_STAGES) p.nstages = TC_MAX_STAGES;
+  if (occ3 && p.nstages > nk_total) p.nstages = nk_total;      // no more ring slots than iterations: smaller CTAs
   if (p.nstages < 2) p.nstages = 2;
   const int smem = p.nstages * p.stage_bytes + 1024 + 256;
   cuuint64_t dimsb[2] = {(cuuint64_t)Ktot, (cuuint64_t)p.Cout};
@@ -967,8 +992,11 @@ static int conv_fwd_tc_impl(const crd_conv_desc* d, const void* x, const void* w
   cuuint32_t boxb[2] = {TC_BK, (cuuint32_t)p.bn};
   rc = make_map(&map_b, w, 2, dimsb, strb, boxb);
   if (rc) return rc;
-  if (cudaError_t le = crd_launch(conv_tc_kernel, dim3(gx, ntile), dim3(TC_THREADS), smem, s, map_a, map_b, p, bias, y,
-                                  gn_sums)) return (int)le;
+  const bool three = occ3 && !am && p.bn <= 128 && (long long)p.nstages * p.stage_bytes + 2048 <= 72 * 1024;
+  if (cudaError_t le = three ? crd_launch(conv_tc_kernel<3>, dim3(gx, ntile), dim3(TC_THREADS), smem, s, map_a, map_b, p,
+                                          bias, y, gn_sums)
+                             : crd_launch(conv_tc_kernel<2>, dim3(gx, ntile), dim3(TC_THREADS), smem, s, map_a, map_b, p,
+                                          bias, y, gn_sums)) return (int)le;
   CRD_LAUNCH_CHECK();
   return 0;
 }
