@@ -167,6 +167,118 @@ __global__ void conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restr
   }
 }
 
+// ---- the production shape (Depth_Activation.conv_2: 32 bf16 channels -> 1) --------------------------------------
+// The generic kernels above / below spend ~1700 (forward) and ~470 (input gradient) instructions per thread on index
+// arithmetic, per-tap weight loads and one load per (tap, 8 channels): ncu showed L1 at 91 % / issue slots at 78 % for
+// 164 MB tensors that stream in 30 us.  These variants share the loads:
+//   forward : a thread owns FOUR adjacent output pixels of a row; per (input row, 8-channel group) it loads the six
+//             input columns once and the 3x8 weights once for 96 FMAs (18 instead of 36 sixteen-byte loads per pixel)
+//   backward: a thread keeps the 9x8 weights of ITS channel group in registers over the whole grid-stride loop and
+//             multiplies by the sigmoid derivative on the way out (no dsg buffer, no separate sigmoid pass)
+constexpr int C1_CIN = 32;
+
+__global__ void __launch_bounds__(256, 2) conv_c1_fwd32_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ y,
+                                                            int B, int H, int W, int ldx) {
+  CRD_PDL_ENTRY();
+  __shared__ __align__(16) float ws[9 * C1_CIN];
+  for (int i = threadIdx.x; i < 9 * C1_CIN; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int Wg = (W + 3) >> 2;
+  const long long total = (long long)B * H * Wg;
+  const float b0 = bias ? bias[0] : 0.f;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total;
+       q += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(q % Wg);
+    const long long bh = q / Wg;                 // b * H + h
+    const int h = (int)(bh % H);
+    const int w0 = g * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const int hh = h + r - 1;
+      if (hh < 0 || hh >= H) continue;
+      const bf16* rowp = x + (bh + (r - 1)) * (long long)W * ldx;
+#pragma unroll
+      for (int cg = 0; cg < C1_CIN / 8; cg++) {
+        uint4 raw[6];
+#pragma unroll
+        for (int d = 0; d < 6; d++) {
+          const int col = w0 + d - 1;
+          raw[d] = (col >= 0 && col < W) ? ldg16(rowp + (long long)col * ldx + cg * 8) : make_uint4(0, 0, 0, 0);
+        }
+        float wr[3][8];
+#pragma unroll
+        for (int kw = 0; kw < 3; kw++) {
+          const float4 lo = *reinterpret_cast<const float4*>(ws + (r * 3 + kw) * C1_CIN + cg * 8);
+          const float4 hi = *reinterpret_cast<const float4*>(ws + (r * 3 + kw) * C1_CIN + cg * 8 + 4);
+          wr[kw][0] = lo.x; wr[kw][1] = lo.y; wr[kw][2] = lo.z; wr[kw][3] = lo.w;
+          wr[kw][4] = hi.x; wr[kw][5] = hi.y; wr[kw][6] = hi.z; wr[kw][7] = hi.w;
+        }
+        float v[6][8];
+#pragma unroll
+        for (int d = 0; d < 6; d++) unpack8(raw[d], v[d]);
+#pragma unroll
+        for (int pz = 0; pz < 4; pz++)
+#pragma unroll
+          for (int kw = 0; kw < 3; kw++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[pz] = fmaf(v[pz + kw][j], wr[kw][j], acc[pz]);
+      }
+    }
+    float* yp = y + bh * W + w0;
+    if (w0 + 3 < W && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
+      *reinterpret_cast<float4*>(yp) = make_float4(acc[0] + b0, acc[1] + b0, acc[2] + b0, acc[3] + b0);
+    } else {
+#pragma unroll
+      for (int pz = 0; pz < 4; pz++)
+        if (w0 + pz < W) yp[pz] = acc[pz] + b0;
+    }
+  }
+}
+
+// dx[pix][c] = (sum_taps dy[pix - tap] w[tap][c]) * (SIG ? s (1 - s) : 1),  s = x[pix][c] (the sigmoid OUTPUT)
+template <bool SIG>
+__global__ void __launch_bounds__(256) conv_c1_bwd_input32_kernel(const float* __restrict__ dy,
+                                                                  const float* __restrict__ w,
+                                                                  const bf16* __restrict__ x, bf16* __restrict__ dx,
+                                                                  int B, int H, int W, int ldx, int lddx) {
+  CRD_PDL_ENTRY();
+  // blockDim and the grid stride are multiples of 4: a thread's channel group never changes
+  const int cv = threadIdx.x & 3;
+  float wreg[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; t++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) wreg[t][j] = w[t * C1_CIN + cv * 8 + j];
+  const long long npix = (long long)B * H * W;
+  for (long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2; pix < npix;
+       pix += ((long long)gridDim.x * blockDim.x) >> 2) {
+    const int ww = (int)(pix % W);
+    const long long bh = pix / W;
+    const int hh = (int)(bh % H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+      const int dh = t / 3 - 1, dw = t % 3 - 1;
+      const int h2 = hh - dh, w2 = ww - dw;
+      const bool ok = (h2 >= 0) & (h2 < H) & (w2 >= 0) & (w2 < W);
+      const float g = ok ? dy[pix - (long long)dh * W - dw] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[j] = fmaf(g, wreg[t][j], acc[j]);
+    }
+    if (SIG) {
+      float sv[8];
+      load8(x + pix * ldx + cv * 8, sv);
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[j] *= sv[j] * (1.f - sv[j]);
+    }
+    store8(dx + pix * lddx + cv * 8, acc);
+  }
+}
+
 template <typename T>
 __global__ void conv_c1_bwd_input_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                          T* __restrict__ dx, int B, int H, int W, int Cin, int lddx) {
@@ -249,6 +361,80 @@ __global__ void conv_c1_bwd_weight_kernel(const float* __restrict__ dy, const T*
       for (int r = 0; r < rows; r++) s += red[r * cvec * 8 + cc];
       if (q < 9) atomicAdd(dw + q * Cin + cc, s);
       else if (db && cc == 0) atomicAdd(db, s * 1.0f);
+    }
+    __syncthreads();
+  }
+}
+
+// Weight gradient of the 32-channel case: dw[tap][c] = sum_q x[q][c] dy[q - tap].  A thread (channel group cv, strip)
+// walks 16 consecutive pixels of one image row with the 3x3 neighbourhood of dy in registers: three new dy values per
+// pixel instead of nine clamped loads (the generic kernel spends ~260 instructions per pixel and channel group).
+constexpr int C1_STRIP = 16;
+__global__ void __launch_bounds__(256, 2) conv_c1_bwd_weight32_kernel(const float* __restrict__ dy,
+                                                                      const bf16* __restrict__ x, float* dw, float* db,
+                                                                      int B, int H, int W, int ldx) {
+  CRD_PDL_ENTRY();
+  __shared__ float red[256 * 8];
+  const int cv = threadIdx.x, ry = threadIdx.y, rows = blockDim.y;       // blockDim = (4, 64)
+  const int spr = (W + C1_STRIP - 1) / C1_STRIP;                           // strips per image row
+  const long long nstrips = (long long)B * H * spr;
+  float acc[10][8];
+#pragma unroll
+  for (int q = 0; q < 10; q++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[q][j] = 0.f;
+  for (long long sidx = (long long)blockIdx.x * rows + ry; sidx < nstrips; sidx += (long long)gridDim.x * rows) {
+    const int sw = (int)(sidx % spr);
+    const long long bh = sidx / spr;                     // b * H + h
+    const int hh = (int)(bh % H);
+    const int w0 = sw * C1_STRIP, w1 = min(W, w0 + C1_STRIP);
+    // G[a][c] = dy[b][hh - 1 + a][ww - 1 + c] (0 outside the image); tap t = (kh, kw) reads G[2 - kh][2 - kw]
+    const float* drow[3];
+    bool rok[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const int h2 = hh - 1 + a;
+      rok[a] = h2 >= 0 && h2 < H;
+      drow[a] = dy + (bh + (a - 1)) * W;
+    }
+    float G[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      G[a][0] = 0.f;
+      G[a][1] = (rok[a] && w0 - 1 >= 0) ? drow[a][w0 - 1] : 0.f;
+      G[a][2] = rok[a] ? drow[a][w0] : 0.f;
+    }
+    const bf16* xp = x + (bh * W + w0) * (long long)ldx + cv * 8;
+    for (int ww = w0; ww < w1; ww++, xp += ldx) {
+      const uint4 raw = ldg16(xp);
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        G[a][0] = G[a][1]; G[a][1] = G[a][2];
+        G[a][2] = (rok[a] && ww + 1 < W) ? drow[a][ww + 1] : 0.f;
+      }
+      float v[8];
+      unpack8(raw, v);
+#pragma unroll
+      for (int t = 0; t < 9; t++) {
+        const float g = G[2 - t / 3][2 - t % 3];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[t][j] = fmaf(g, v[j], acc[t][j]);
+      }
+      if (cv == 0) acc[9][0] += G[1][1];
+    }
+  }
+  const int cvec = 4, Cin = C1_CIN;
+#pragma unroll
+  for (int q = 0; q < 10; q++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) red[(ry * cvec + cv) * 8 + j] = acc[q][j];
+    __syncthreads();
+    const int t = ry * cvec + cv, nt = rows * cvec;
+    for (int cc = t; cc < Cin; cc += nt) {
+      float sum = 0.f;
+      for (int r = 0; r < rows; r++) sum += red[r * cvec * 8 + cc];
+      if (q < 9) atomicAdd(dw + q * Cin + cc, sum);
+      else if (db && cc == 0) atomicAdd(db, sum);
     }
     __syncthreads();
   }
@@ -521,28 +707,60 @@ extern "C" int crd_bicubic2x_bwd(const void* dy, void* dx, int dtype, int accumu
   CRD_LAUNCH_CHECK();
   return 0;
 }
+static bool c1_fast() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("CAMRADEPTH_C1_FAST"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
 extern "C" int crd_conv3x3_c1_fwd(const void* x, int dtype, const float* w, const float* bias, float* y, int B,
                                   int H, int W, int Cin, int ldx, crd_stream_t stream) {
   CRD_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0 && Cin <= 1024);
   const long long total = (long long)B * H * W;
   if (total == 0) return 0;
+  if (dtype == CRD_BF16 && Cin == C1_CIN && c1_fast() && ((uintptr_t)x & 15) == 0) {
+    const long long quads = (long long)B * H * ((W + 3) / 4);
+    crd_launch(conv_c1_fwd32_kernel, dim3(ew_blocks(quads)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, w,
+               bias, y, B, H, W, ldx);
+    CRD_LAUNCH_CHECK();
+    return 0;
+  }
   CRD_DISPATCH_1(dtype, T, crd_launch(conv_c1_fwd_kernel<T>, dim3(ew_blocks(total)), dim3(256), 9 * Cin * sizeof(float), (cudaStream_t)stream, (const T*)x, w, bias, y, B, H, W, Cin, ldx));
   CRD_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int crd_conv3x3_c1_bwd(const float* dy, const void* x, int dtype, const float* w, void* dx, float* dw,
-                                  float* db, int B, int H, int W, int Cin, int ldx, int lddx,
-                                  crd_stream_t stream) {
+static int conv3x3_c1_bwd_impl(const float* dy, const void* x, int dtype, const float* w, void* dx, float* dw,
+                               float* db, int B, int H, int W, int Cin, int ldx, int lddx, int sig,
+                               crd_stream_t stream) {
   CRD_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0 && Cin / 8 <= 256);
   const long long total = (long long)B * H * W * (Cin / 8);
   if (total == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (dx) {
+  if (dx && dtype == CRD_BF16 && Cin == C1_CIN && c1_fast() && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dx & 15) == 0) {
+    if (sig) crd_launch(conv_c1_bwd_input32_kernel<true>, dim3(ew_blocks(total)), dim3(256), 0, s, dy, w, (const bf16*)x,
+                        (bf16*)dx, B, H, W, ldx, lddx);
+    else crd_launch(conv_c1_bwd_input32_kernel<false>, dim3(ew_blocks(total)), dim3(256), 0, s, dy, w, (const bf16*)x,
+                    (bf16*)dx, B, H, W, ldx, lddx);
+    CRD_LAUNCH_CHECK();
+  } else if (dx) {
     CRD_DISPATCH_1(dtype, T, crd_launch(conv_c1_bwd_input_kernel<T>, dim3(ew_blocks(total)), dim3(256), 0, s, 
                                  dy, w, (T*)dx, B, H, W, Cin, lddx));
     CRD_LAUNCH_CHECK();
+    if (sig) {            // generic route: the separate sigmoid-derivative pass, in place (needs a dense dx)
+      CRD_REQUIRE(lddx == Cin && ldx == Cin);
+      CRD_DISPATCH_1(dtype, T, crd_launch(sigmoid_bwd_kernel<T>, dim3(ew_blocks(total)), dim3(256), 0, s, (const T*)dx,
+                                          (const T*)x, (T*)dx, total));
+      CRD_LAUNCH_CHECK();
+    }
   }
-  if (dw) {
+  if (dw && dtype == CRD_BF16 && Cin == C1_CIN && c1_fast() && ((uintptr_t)x & 15) == 0) {
+    const long long nstrips = (long long)B * H * ((W + C1_STRIP - 1) / C1_STRIP);
+    long long blocks = (nstrips + 63) / 64;
+    const long long cap = 2LL * sm_count();                 // two resident blocks per SM, grid-stride beyond that
+    if (blocks > cap) blocks = cap;
+    crd_launch(conv_c1_bwd_weight32_kernel, dim3((unsigned)blocks), dim3(4, 64), 0, s, dy, (const bf16*)x, dw, db, B, H, W,
+               ldx);
+    CRD_LAUNCH_CHECK();
+  } else if (dw) {
     ReduceLaunch r = plan_reduce(B, (long long)H * W, Cin);
     const size_t smem = (size_t)r.block.x * r.block.y * 8 * sizeof(float);
     CRD_DISPATCH_1(dtype, T, crd_launch(conv_c1_bwd_weight_kernel<T>, dim3(r.grid), dim3(r.block), smem, s, 
@@ -550,6 +768,19 @@ extern "C" int crd_conv3x3_c1_bwd(const float* dy, const void* x, int dtype, con
     CRD_LAUNCH_CHECK();
   }
   return 0;
+}
+extern "C" int crd_conv3x3_c1_bwd(const float* dy, const void* x, int dtype, const float* w, void* dx, float* dw,
+                                  float* db, int B, int H, int W, int Cin, int ldx, int lddx,
+                                  crd_stream_t stream) {
+  return conv3x3_c1_bwd_impl(dy, x, dtype, w, dx, dw, db, B, H, W, Cin, ldx, lddx, 0, stream);
+}
+// as crd_conv3x3_c1_bwd with x = the OUTPUT of the sigmoid that feeds the conv (Depth_Activation, utils.py:285-289):
+// dx receives the gradient with respect to the sigmoid's INPUT, dx = dgrad * x * (1 - x)
+extern "C" int crd_conv3x3_c1_bwd_sigmoid(const float* dy, const void* x, int dtype, const float* w, void* dx,
+                                          float* dw, float* db, int B, int H, int W, int Cin, int ldx, int lddx,
+                                          crd_stream_t stream) {
+  CRD_REQUIRE(dx != nullptr);
+  return conv3x3_c1_bwd_impl(dy, x, dtype, w, dx, dw, db, B, H, W, Cin, ldx, lddx, 1, stream);
 }
 extern "C" int crd_sigmoid_bwd(const void* dy, const void* y, void* dx, int dtype, long long n,
                                crd_stream_t stream) {

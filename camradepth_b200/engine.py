@@ -726,12 +726,11 @@ class Engine:
         L = self.L[name + ".conv_1.weight"]
         sg, F = rec["sg"], rec["F"]
         w2 = self.wpack(name + ".conv_2.weight", 0, dtype=torch.float32)
-        dsg = self._empty(*sg.shape)
-        dw2 = self.bwd_arena.take(1, 9 * 32)
-        ops.conv3x3_c1_bwd(ddepth, sg, w2, dsg, dw2, self.pg[name + ".conv_2.bias"])
-        ops.weight_unpack_grad(dw2, self.pg[name + ".conv_2.weight"], None, 1, 32, 9, 32, False)
         dpre = self._empty(*sg.shape)
-        ops.sigmoid_bwd(dsg, sg, dpre)
+        dw2 = self.bwd_arena.take(1, 9 * 32)
+        # data gradient of conv_2 times the sigmoid derivative in one pass (no dsg buffer)
+        ops.conv3x3_c1_bwd_sigmoid(ddepth, sg, w2, dpre, dw2, self.pg[name + ".conv_2.bias"])
+        ops.weight_unpack_grad(dw2, self.pg[name + ".conv_2.weight"], None, 1, 32, 9, 32, False)
         self.conv_wgrad(F[..., :L["cin_p"]], dpre, name + ".conv_1.weight", bias=name + ".conv_1.bias")
         self.conv_dgrad(dpre, name + ".conv_1.weight", dF[..., :L["cin_p"]], accumulate)
 

@@ -314,6 +314,13 @@ def conv3x3_c1_bwd(dy, x, w, dx, dw, db):
                          _ld(dx) if dx is not None else 8, stream())
 
 
+def conv3x3_c1_bwd_sigmoid(dy, x, w, dx, dw, db):
+    """conv3x3_c1_bwd whose dx is the gradient wrt the INPUT of the sigmoid that produced x (dgrad * x * (1 - x))."""
+    B, H, W, C = x.shape
+    K.crd_conv3x3_c1_bwd_sigmoid(P(dy), P(x), dcode(x), P(w), P(dx), P(dw), P(db), B, H, W, C, _ld(x), _ld(dx),
+                                 stream())
+
+
 def sigmoid_bwd(dy, y, dx):
     assert dy.is_contiguous() and y.is_contiguous() and dx.is_contiguous()
     K.crd_sigmoid_bwd(P(dy), P(y), P(dx), dcode(y), y.numel(), stream())

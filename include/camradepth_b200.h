@@ -217,6 +217,10 @@ CRD_API int crd_conv3x3_c1_fwd(const void* x, int dtype, const float* w /*[9][Ci
                        int B, int H, int W, int Cin, int ldx, crd_stream_t stream);
 CRD_API int crd_conv3x3_c1_bwd(const float* dy, const void* x, int dtype, const float* w, void* dx, float* dw,
                        float* db, int B, int H, int W, int Cin, int ldx, int lddx, crd_stream_t stream);
+/* same, with x = the OUTPUT of the sigmoid that feeds this conv (Depth_Activation, utils.py:285-289): dx receives the
+ * gradient with respect to the sigmoid's INPUT, dx = dgrad * x * (1 - x) (one launch for the 32-channel bf16 case) */
+CRD_API int crd_conv3x3_c1_bwd_sigmoid(const float* dy, const void* x, int dtype, const float* w, void* dx, float* dw,
+                               float* db, int B, int H, int W, int Cin, int ldx, int lddx, crd_stream_t stream);
 /* dx = dy * y * (1-y) (y = sigmoid output) */
 CRD_API int crd_sigmoid_bwd(const void* dy, const void* y, void* dx, int dtype, long long n, crd_stream_t stream);
 /* Seg_Block (utils.py:95-100): map = argmax_c(logits)/ncls ; written to a channel of an NHWC buffer and/or

@@ -403,6 +403,18 @@ def test_depth_head_stencil_sigmoid_argmax(dtype):
     gwu = torch.empty_like(w)
     ops.weight_unpack_grad(dw, gwu, None, 1, C, 9, C, False)
     assert rel(nchw(dx), gx) < TOL[dtype] and rel(gwu, gw) < 1e-4 and rel(db, gy.sum().view(1)) < 1e-4
+    # fused form used by Depth_Activation: x is a sigmoid output, dx the gradient wrt the sigmoid's input
+    dxs = torch.empty(B, H, W, C, dtype=dtype, device=d)
+    dw_s, db_s = torch.zeros(1, 9 * C, device=d), torch.zeros(1, device=d)
+    ops.conv3x3_c1_bwd_sigmoid(gy, xb, wp, dxs, dw_s, db_s)
+    xq = rnd(x, dtype)
+    assert rel(nchw(dxs), gx * xq * (1 - xq)) < TOL[dtype]
+    assert rel(dw_s, dw) < 1e-6 and rel(db_s, db) < 1e-6
+    # a wide, ragged image (W % 4 != 0) through the four-pixels-per-thread forward kernel
+    x2 = torch.rand(1, C, 5, 23, device=d)
+    y2 = torch.empty(1, 1, 5, 23, device=d)
+    ops.conv3x3_c1_fwd(nhwc(x2, dtype), wp, bias, y2)
+    assert rel(y2, F.conv2d(rnd(x2, dtype), w, bias, padding=1)) < 1e-5
     # sigmoid backward
     sg = torch.sigmoid(x)
     g = torch.randn_like(x)

@@ -40,6 +40,11 @@ ab)     # A/B of engine switches: AB="CAMRADEPTH_SPLIT=;CAMRADEPTH_LEAF_STAGES="
 det)    timeout 300 python tools/det_check.py ${DET_VARIANT:-base} > gpurun_out/${TAG}_det_check.txt 2>&1; tail -20 gpurun_out/${TAG}_det_check.txt ;;
 dp2)    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_check.py supervised_seg fp32 > gpurun_out/${TAG}_dp_check.txt 2>&1; tail -4 gpurun_out/${TAG}_dp_check.txt
         timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/dp_check.py base bf16 >> gpurun_out/${TAG}_dp_check.txt 2>&1; tail -3 gpurun_out/${TAG}_dp_check.txt ;;
+ncu_k)  # full-set ncu capture of the kernels matching NCU_K (regex) inside one eager training step
+        timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCU_K}" -c ${NCU_C:-9} -o gpurun_out/${TAG}_prof_k -f python bench.py --steps 1 --warmup 1 --quick --no-graph > gpurun_out/${TAG}_ncu_k.log 2>&1; tail -3 gpurun_out/${TAG}_ncu_k.log
+        ncu -i gpurun_out/${TAG}_prof_k.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_k_raw.csv 2>/dev/null
+        ncu -i gpurun_out/${TAG}_prof_k.ncu-rep --page details --csv > gpurun_out/${TAG}_ncu_k_details.csv 2>/dev/null
+        [ $(stat -c %s gpurun_out/${TAG}_prof_k.ncu-rep) -gt 25000000 ] && rm -f gpurun_out/${TAG}_prof_k.ncu-rep ;;
 ablib)  # same-box A/B of library builds: ABLIBS="ab_libs/lib_head.so ab_libs/lib_lane0.so default"
         for L in ${ABLIBS}; do
           echo "==== ${L}" >> gpurun_out/${TAG}_ablib.txt
