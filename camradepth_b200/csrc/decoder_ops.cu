@@ -178,62 +178,61 @@ __global__ void conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restr
 constexpr int C1_CIN = 32;
 
 __global__ void __launch_bounds__(256, 2) conv_c1_fwd32_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
-                                                            const float* __restrict__ bias, float* __restrict__ y,
-                                                            int B, int H, int W, int ldx) {
+                                                               const float* __restrict__ bias, float* __restrict__ y,
+                                                               int B, int H, int W, int ldx) {
   CRD_PDL_ENTRY();
-  __shared__ __align__(16) float ws[9 * C1_CIN];
-  for (int i = threadIdx.x; i < 9 * C1_CIN; i += blockDim.x) ws[i] = w[i];
-  __syncthreads();
+  // four lanes per pixel quad, one per 8-channel group: a warp's 16-byte loads of one (row, column) cover 8 runs of
+  // 64 contiguous bytes (with one lane per quad they were 32 separate lines per load: L1 at 84-91 %), and the lane's
+  // 9x8 weights stay in registers for the whole grid-stride loop (no shared memory)
+  const int lane = threadIdx.x & 31, cg = lane & 3;
+  float wreg[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; t++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) wreg[t][j] = w[t * C1_CIN + cg * 8 + j];
   const int Wg = (W + 3) >> 2;
   const long long total = (long long)B * H * Wg;
   const float b0 = bias ? bias[0] : 0.f;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total;
-       q += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(q % Wg);
-    const long long bh = q / Wg;                 // b * H + h
+  const long long stride_q = ((long long)gridDim.x * blockDim.x) >> 2;
+  for (long long q0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2) - (lane >> 2); q0 < total;
+       q0 += stride_q) {                                  // q0 is warp-uniform: the shuffles below see all lanes
+    const long long q = q0 + (lane >> 2);
+    const bool qok = q < total;
+    const long long qq = qok ? q : 0;
+    const int g = (int)(qq % Wg);
+    const long long bh = qq / Wg;                // b * H + h
     const int h = (int)(bh % H);
     const int w0 = g * 4;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int r = 0; r < 3; r++) {
       const int hh = h + r - 1;
-      if (hh < 0 || hh >= H) continue;
-      const bf16* rowp = x + (bh + (r - 1)) * (long long)W * ldx;
+      if (!qok || hh < 0 || hh >= H) continue;
+      const bf16* rowp = x + (bh + (r - 1)) * (long long)W * ldx + cg * 8;
+      uint4 raw[6];
 #pragma unroll
-      for (int cg = 0; cg < C1_CIN / 8; cg++) {
-        uint4 raw[6];
-#pragma unroll
-        for (int d = 0; d < 6; d++) {
-          const int col = w0 + d - 1;
-          raw[d] = (col >= 0 && col < W) ? ldg16(rowp + (long long)col * ldx + cg * 8) : make_uint4(0, 0, 0, 0);
-        }
-        float wr[3][8];
-#pragma unroll
-        for (int kw = 0; kw < 3; kw++) {
-          const float4 lo = *reinterpret_cast<const float4*>(ws + (r * 3 + kw) * C1_CIN + cg * 8);
-          const float4 hi = *reinterpret_cast<const float4*>(ws + (r * 3 + kw) * C1_CIN + cg * 8 + 4);
-          wr[kw][0] = lo.x; wr[kw][1] = lo.y; wr[kw][2] = lo.z; wr[kw][3] = lo.w;
-          wr[kw][4] = hi.x; wr[kw][5] = hi.y; wr[kw][6] = hi.z; wr[kw][7] = hi.w;
-        }
-        float v[6][8];
-#pragma unroll
-        for (int d = 0; d < 6; d++) unpack8(raw[d], v[d]);
-#pragma unroll
-        for (int pz = 0; pz < 4; pz++)
-#pragma unroll
-          for (int kw = 0; kw < 3; kw++)
-#pragma unroll
-            for (int j = 0; j < 8; j++) acc[pz] = fmaf(v[pz + kw][j], wr[kw][j], acc[pz]);
+      for (int d = 0; d < 6; d++) {
+        const int col = w0 + d - 1;
+        raw[d] = (col >= 0 && col < W) ? ldg16(rowp + (long long)col * ldx) : make_uint4(0, 0, 0, 0);
       }
-    }
-    float* yp = y + bh * W + w0;
-    if (w0 + 3 < W && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
-      *reinterpret_cast<float4*>(yp) = make_float4(acc[0] + b0, acc[1] + b0, acc[2] + b0, acc[3] + b0);
-    } else {
+      float v[6][8];
+#pragma unroll
+      for (int d = 0; d < 6; d++) unpack8(raw[d], v[d]);
 #pragma unroll
       for (int pz = 0; pz < 4; pz++)
-        if (w0 + pz < W) yp[pz] = acc[pz] + b0;
+#pragma unroll
+        for (int kw = 0; kw < 3; kw++)
+#pragma unroll
+          for (int j = 0; j < 8; j++) acc[pz] = fmaf(v[pz + kw][j], wreg[r * 3 + kw][j], acc[pz]);
     }
+#pragma unroll
+    for (int pz = 0; pz < 4; pz++) {
+      acc[pz] += __shfl_xor_sync(0xffffffffu, acc[pz], 1);
+      acc[pz] += __shfl_xor_sync(0xffffffffu, acc[pz], 2);
+    }
+    // lane cg stores pixel w0 + cg: 32 consecutive floats per warp
+    const float mine = cg == 0 ? acc[0] : (cg == 1 ? acc[1] : (cg == 2 ? acc[2] : acc[3]));
+    if (qok && w0 + cg < W) y[bh * W + w0 + cg] = mine + b0;
   }
 }
 
@@ -257,6 +256,7 @@ __global__ void __launch_bounds__(256) conv_c1_bwd_input32_kernel(const float* _
     const int ww = (int)(pix % W);
     const long long bh = pix / W;
     const int hh = (int)(bh % H);
+    const float* dyp = dy + pix;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[j] = 0.f;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) conv_c1_bwd_input32_kernel(const float* _
       const int dh = t / 3 - 1, dw = t % 3 - 1;
       const int h2 = hh - dh, w2 = ww - dw;
       const bool ok = (h2 >= 0) & (h2 < H) & (w2 >= 0) & (w2 < W);
-      const float g = ok ? dy[pix - (long long)dh * W - dw] : 0.f;
+      const float g = ok ? dyp[-(dh * W + dw)] : 0.f;
 #pragma unroll
       for (int j = 0; j < 8; j++) acc[j] = fmaf(g, wreg[t][j], acc[j]);
     }
@@ -719,7 +719,7 @@ extern "C" int crd_conv3x3_c1_fwd(const void* x, int dtype, const float* w, cons
   if (total == 0) return 0;
   if (dtype == CRD_BF16 && Cin == C1_CIN && c1_fast() && ((uintptr_t)x & 15) == 0) {
     const long long quads = (long long)B * H * ((W + 3) / 4);
-    crd_launch(conv_c1_fwd32_kernel, dim3(ew_blocks(quads)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, w,
+    crd_launch(conv_c1_fwd32_kernel, dim3(ew_blocks(quads * 4)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, w,
                bias, y, B, H, W, ldx);
     CRD_LAUNCH_CHECK();
     return 0;
