@@ -192,7 +192,7 @@ class Engine:
         """Feature buffer [feat 128 | depth | seg maps | pad]: the 128 feature channels are fully written by the
         decoder block, so only the tail channels are zero-filled (a full fill of the 192x416 buffer is 0.7 GB)."""
         t = self._empty(B, H, W, FW)
-        t[..., MID:].zero_()
+        ops.zero_channels(t[..., MID:])
         return t
 
     def _zeros(self, *shape, dtype=None):
@@ -248,14 +248,16 @@ class Engine:
             for (name, dst, cmap, cout, cin, taps, cin_p, cout_p, mode) in jobs:
                 ops.weight_pack(self.P[name].detach(), dst, cmap, cout, cin, taps, cin_p, cout_p, mode)
         elif self._pack_table is None or self._pack_table[0] != sig:
-            rows, blk = [], 0
-            for (name, dst, cmap, cout, cin, taps, cin_p, cout_p, mode) in jobs:
+            rows, blk, owner = [], 0, []
+            for it, (name, dst, cmap, cout, cin, taps, cin_p, cout_p, mode) in enumerate(jobs):
                 total = cout * cin * taps
                 rows.append([self.P[name].data_ptr(), dst.data_ptr(), 0 if cmap is None else cmap.data_ptr(), blk,
                              cout, cin, taps, cin_p, cout_p, mode, ops.dcode(dst), total])
-                blk += (total + 1023) // 1024
+                nb = ops.weight_pack_blocks(cout, cin, taps)
+                owner += [it] * nb
+                blk += nb
             rows.append([0, 0, 0, blk] + [0] * 8)
-            table = torch.tensor(rows, dtype=torch.int64).to(self.device)
+            table = torch.tensor([v for r in rows for v in r] + owner, dtype=torch.int64).to(self.device)
             self._pack_table = (sig, table, len(jobs), blk)
         if self._pack_table is not None and self._pack_table[0] == sig:
             _, table, n, blk = self._pack_table
@@ -872,7 +874,9 @@ class Engine:
             else:
                 ops.nchw_to_nhwc(x, cat[..., MID + 1:MID + 1 + cin])
 
-        F5 = self._feat(B, H, W, FW)
+        # the last feature map feeds only the heads: without seg maps nothing reads its tail channels
+        da5_w = self.L["depth_activation_5.conv_1.weight"]["cin_p"]
+        F5 = self._empty(B, H, W, MID) if (not seg and da5_w == MID) else self._feat(B, H, W, FW)
         S["D4"] = self.dec_fwd("depth_upsample.4", F4, skip_input, F5[..., :MID], d2[5 if seg else 4], save)
         final_seg = unsup_map = None
         if seg:
@@ -956,9 +960,10 @@ class Engine:
         # the depth head's data gradient (accumulate=False) overwrites every channel it reads; a zero fill is only
         # needed when the buffer is wider than that
         da5_w = self.L["depth_activation_5.conv_1.weight"]["cin_p"]
-        dF5 = self._empty(B, H, W, FW)
-        if da5_w != FW:
-            dF5[..., da5_w:].zero_()          # only the tail channels: a full fill of this buffer is 0.7 GB at batch 32
+        # only dF5[..., :MID] is consumed below (the decoder's output channels): no tail, no fill
+        dF5 = self._empty(B, H, W, max(da5_w, MID))
+        if da5_w < MID:
+            ops.zero_channels(dF5[..., da5_w:])
         self.da_bwd("depth_activation_5", S["DA5"], gz(g_final, (B, 1, H, W)), dF5, False)
         sup_grad = cfg.sup and g_seg is not None
         dFS4 = None

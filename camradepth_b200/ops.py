@@ -128,6 +128,20 @@ def weight_pack(w, dst, cmap, Cout, Cin, taps, Cin_p, Cout_p, mode):
     K.crd_weight_pack(P(w), P(dst), dcode(dst), P(cmap), Cout, Cin, taps, Cin_p, Cout_p, mode, stream())
 
 
+def zero_channels(view):
+    """Zero a channel slice view[..., a:b] of an NHWC buffer (last dim contiguous)."""
+    C = view.shape[-1]
+    K.crd_zero_channels(P(view), _ld(view), dcode(view), C, view.numel() // max(C, 1), stream())
+
+
+def weight_pack_blocks(cout, cin, taps):
+    """Blocks one item of a weight_pack_batch table owns."""
+    n = load().crd_weight_pack_blocks(cout, cin, taps)
+    if n <= 0:
+        raise ValueError(f"weight_pack_batch cannot take Cout={cout} Cin={cin} taps={taps}")
+    return n
+
+
 def weight_pack_batch(table, n_items, n_blocks):
     K.crd_weight_pack_batch(P(table), n_items, n_blocks, stream())
 

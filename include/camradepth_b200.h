@@ -105,7 +105,14 @@ CRD_API int crd_weight_pack(const float* w, void* dst, int dst_dtype, const int*
                     int Cin_p, int Cout_p, int mode, crd_stream_t stream);
 /* All packed copies in one launch (refresh after an optimizer step, runner.py:232).  `table` is a DEVICE array of
  * n_items + 1 rows of 12 int64: {w, dst, map, first block, Cout, Cin, taps, Cin_p, Cout_p, mode, dst dtype,
- * Cout*Cin*taps}; an item owns ceil(elements / 1024) consecutive blocks and row n_items holds n_blocks. */
+ * Cout*Cin*taps}; an item owns crd_weight_pack_blocks(Cout, Cin, taps) consecutive blocks (one per brick of output
+ * channels x input channels x all taps; taps <= 128) and row n_items holds n_blocks; the rows are followed by n_blocks
+ * int64 values, the item index of every block. */
+CRD_API int crd_weight_pack_blocks(int Cout, int Cin, int taps);
+/* dst[pix][0..C) = 0 for npix pixels of an NHWC buffer with pixel stride ld (dst points at the first channel to clear):
+ * the zero padding / not-yet-written tail channels of the feature buffers ([features | depth | seg maps | pad],
+ * CamRaDepth.py:137-162), without filling the whole buffer */
+CRD_API int crd_zero_channels(void* dst, int ld, int dtype, int C, long long npix, crd_stream_t stream);
 CRD_API int crd_weight_pack_batch(const long long* table, int n_items, int n_blocks, crd_stream_t stream);
 /* Strided convolutions (patch embeddings k7s4/k3s2, spatial-reduction convs k=s; simplified_attention.py:68,
  * 158-160) run as GEMMs on the tensor-core path: gather the patches once, multiply, scatter the data gradient.

@@ -433,6 +433,50 @@ def test_depth_head_stencil_sigmoid_argmax(dtype):
     assert float(buf[..., :129].abs().max()) == 0
 
 
+def test_weight_pack_batch_matches_per_tensor_pack():
+    """One-launch packing (bricks through shared memory) == the per-tensor kernel, all three layouts, with and without
+    a channel map, ragged bricks, 7x7 taps."""
+    from camradepth_b200 import ops
+    d = dev()
+    torch.manual_seed(11)
+    cases = [(96, 136, 9, 0, False), (136, 96, 9, 1, False), (128, 296, 9, 0, True), (64, 7, 49, 0, False),
+             (160, 160, 4, 2, False), (1024, 128, 1, 1, False), (21, 128, 9, 0, False), (33, 70, 9, 1, True)]
+    rows, blk, keep, owner = [], 0, [], []
+    for (cout, cin, taps, mode, use_map) in cases:
+        w = torch.randn(cout, cin, taps, device=d)
+        cin_p, cout_p = r8(cin) + (8 if use_map else 0), r8(cout)
+        cmap = (torch.randperm(cin_p, device=d)[:cin].to(torch.int32).contiguous()) if use_map else None
+        shape = (cout, taps * cin_p) if mode == 0 else ((cin_p, taps * cout_p) if mode == 1 else (taps * cin_p, cout_p))
+        for dt in (torch.bfloat16, torch.float32):
+            ref = torch.zeros(shape, dtype=dt, device=d)
+            ops.weight_pack(w, ref, cmap, cout, cin, taps, cin_p, cout_p, mode)
+            dst = torch.zeros(shape, dtype=dt, device=d)
+            rows.append([w.data_ptr(), dst.data_ptr(), 0 if cmap is None else cmap.data_ptr(), blk, cout, cin, taps,
+                         cin_p, cout_p, mode, ops.dcode(dst), cout * cin * taps])
+            nb = ops.weight_pack_blocks(cout, cin, taps)
+            owner += [len(rows) - 1] * nb
+            blk += nb
+            keep.append((w, cmap, ref, dst))
+    rows.append([0, 0, 0, blk] + [0] * 8)
+    table = torch.tensor([v for r in rows for v in r] + owner, dtype=torch.int64).to(d)
+    ops.weight_pack_batch(table, len(rows) - 1, blk)
+    torch.cuda.synchronize()
+    for (_, _, ref, dst) in keep:
+        assert torch.equal(ref, dst)
+
+
+def test_zero_channels():
+    from camradepth_b200 import ops
+    d = dev()
+    for dt in DT:
+        for (ld, a, b) in ((136, 128, 136), (136, 129, 136), (24, 21, 24), (320, 296, 320)):
+            t = torch.full((3, 5, 7, ld), 3.0, dtype=dt, device=d)
+            ops.zero_channels(t[..., a:b])
+            assert float(t[..., a:b].abs().max()) == 0 and float((t[..., :a] - 3).abs().max()) == 0
+            if b < ld:
+                assert float((t[..., b:] - 3).abs().max()) == 0
+
+
 def test_layout_roundtrip():
     from camradepth_b200 import ops
     d = dev()
