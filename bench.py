@@ -270,7 +270,15 @@ def measure_train(variant, a, dev, rank, world, local, headline):
     barrier(world)
     if sampler:
         sampler.start()
+    # CAMRADEPTH_PROFILE_TIMED=1 (with `ncu --profile-from-start off`): only the timed steps are instrumented, so a
+    # launch list of one step costs one step's worth of replays instead of the warm-up's as well
+    prof = os.environ.get("CAMRADEPTH_PROFILE_TIMED", "0") == "1"
+    if prof:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
     ms = timed_region(run_resident, steps, world)
+    if prof:
+        torch.cuda.cudart().cudaProfilerStop()
     if sampler:
         sampler.stop_flag = True
     res = {"ms": ms, "steps": steps, "T": T, "sampler": sampler, "graphs": len(g.graphs) if use_graph else 0}

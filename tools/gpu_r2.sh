@@ -25,8 +25,8 @@ ncu_enc) ENC_STAGES=${ENC_STAGES:-2} timeout 900 ncu --set full --clock-control 
 enc)    ENC_TIME=1 timeout 300 python tools/run_encoder_for_ncu.py > gpurun_out/${TAG}_encoder_gemms.txt 2>&1; tail -40 gpurun_out/${TAG}_encoder_gemms.txt
         echo "---- CAMRADEPTH_TC_PIPE=0" >> gpurun_out/${TAG}_encoder_gemms.txt
         CAMRADEPTH_TC_PIPE=0 ENC_TIME=1 ENC_STAGES=1,2 timeout 300 python tools/run_encoder_for_ncu.py >> gpurun_out/${TAG}_encoder_gemms.txt 2>&1; tail -20 gpurun_out/${TAG}_encoder_gemms.txt ;;
-launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 14000 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --quick --no-graph > gpurun_out/${TAG}_launches.log 2>&1
-        python profiles/summarize_launches.py gpurun_out/${TAG}_launches.csv 70 last_step > gpurun_out/${TAG}_launches_summary.txt 2>&1; head -30 gpurun_out/${TAG}_launches_summary.txt ;;
+launches) CAMRADEPTH_PROFILE_TIMED=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --quick --no-graph > gpurun_out/${TAG}_launches.log 2>&1
+        python profiles/summarize_launches.py gpurun_out/${TAG}_launches.csv 70 > gpurun_out/${TAG}_launches_summary.txt 2>&1; head -30 gpurun_out/${TAG}_launches_summary.txt ;;
 step)   timeout 300 python tools/profile_step.py --batch 32 > gpurun_out/${TAG}_step_profile.txt 2>&1; head -40 gpurun_out/${TAG}_step_profile.txt ;;
 convs)  timeout 300 python tools/profile_convs.py 32 > gpurun_out/${TAG}_conv_profile.txt 2>&1; tail -30 gpurun_out/${TAG}_conv_profile.txt ;;
 ew)     timeout 300 python tools/bench_elementwise.py > gpurun_out/${TAG}_elementwise.txt 2>&1 ;;
