@@ -185,11 +185,11 @@ __global__ void __launch_bounds__(256, 2) conv_c1_fwd32_kernel(const bf16* __res
   // 64 contiguous bytes (with one lane per quad they were 32 separate lines per load: L1 at 84-91 %), and the lane's
   // 9x8 weights stay in registers for the whole grid-stride loop (no shared memory)
   const int lane = threadIdx.x & 31, cg = lane & 3;
-  float wreg[9][8];
+  float2 wreg[9][4];                      // channel pairs: even / odd channels accumulate in the halves of one FFMA2
 #pragma unroll
   for (int t = 0; t < 9; t++)
 #pragma unroll
-    for (int j = 0; j < 8; j++) wreg[t][j] = w[t * C1_CIN + cg * 8 + j];
+    for (int j = 0; j < 4; j++) wreg[t][j] = make_float2(w[t * C1_CIN + cg * 8 + 2 * j], w[t * C1_CIN + cg * 8 + 2 * j + 1]);
   const int Wg = (W + 3) >> 2;
   const long long total = (long long)B * H * Wg;
   const float b0 = bias ? bias[0] : 0.f;
@@ -203,7 +203,9 @@ __global__ void __launch_bounds__(256, 2) conv_c1_fwd32_kernel(const bf16* __res
     const long long bh = qq / Wg;                // b * H + h
     const int h = (int)(bh % H);
     const int w0 = g * 4;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float2 acc2[4];
+#pragma unroll
+    for (int pz = 0; pz < 4; pz++) acc2[pz] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < 3; r++) {
       const int hh = h + r - 1;
@@ -215,18 +217,25 @@ __global__ void __launch_bounds__(256, 2) conv_c1_fwd32_kernel(const bf16* __res
         const int col = w0 + d - 1;
         raw[d] = (col >= 0 && col < W) ? ldg16(rowp + (long long)col * ldx) : make_uint4(0, 0, 0, 0);
       }
-      float v[6][8];
+      float2 v[6][4];
 #pragma unroll
-      for (int d = 0; d < 6; d++) unpack8(raw[d], v[d]);
+      for (int d = 0; d < 6; d++) {
+        float t8[8];
+        unpack8(raw[d], t8);
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[d][j] = make_float2(t8[2 * j], t8[2 * j + 1]);
+      }
 #pragma unroll
       for (int pz = 0; pz < 4; pz++)
 #pragma unroll
         for (int kw = 0; kw < 3; kw++)
 #pragma unroll
-          for (int j = 0; j < 8; j++) acc[pz] = fmaf(v[pz + kw][j], wreg[r * 3 + kw][j], acc[pz]);
+          for (int j = 0; j < 4; j++) acc2[pz] = __ffma2_rn(v[pz + kw][j], wreg[r * 3 + kw][j], acc2[pz]);
     }
+    float acc[4];
 #pragma unroll
     for (int pz = 0; pz < 4; pz++) {
+      acc[pz] = acc2[pz].x + acc2[pz].y;
       acc[pz] += __shfl_xor_sync(0xffffffffu, acc[pz], 1);
       acc[pz] += __shfl_xor_sync(0xffffffffu, acc[pz], 2);
     }
@@ -245,11 +254,11 @@ __global__ void __launch_bounds__(256) conv_c1_bwd_input32_kernel(const float* _
   CRD_PDL_ENTRY();
   // blockDim and the grid stride are multiples of 4: a thread's channel group never changes
   const int cv = threadIdx.x & 3;
-  float wreg[9][8];
+  float2 wreg[9][4];                      // channel pairs: the taps run on FFMA2
 #pragma unroll
   for (int t = 0; t < 9; t++)
 #pragma unroll
-    for (int j = 0; j < 8; j++) wreg[t][j] = w[t * C1_CIN + cv * 8 + j];
+    for (int j = 0; j < 4; j++) wreg[t][j] = make_float2(w[t * C1_CIN + cv * 8 + 2 * j], w[t * C1_CIN + cv * 8 + 2 * j + 1]);
   const long long npix = (long long)B * H * W;
   for (long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2; pix < npix;
        pix += ((long long)gridDim.x * blockDim.x) >> 2) {
@@ -257,9 +266,9 @@ __global__ void __launch_bounds__(256) conv_c1_bwd_input32_kernel(const float* _
     const long long bh = pix / W;
     const int hh = (int)(bh % H);
     const float* dyp = dy + pix;
-    float acc[8];
+    float2 acc2[4];
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+    for (int j = 0; j < 4; j++) acc2[j] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int t = 0; t < 9; t++) {
       const int dh = t / 3 - 1, dw = t % 3 - 1;
@@ -267,8 +276,11 @@ __global__ void __launch_bounds__(256) conv_c1_bwd_input32_kernel(const float* _
       const bool ok = (h2 >= 0) & (h2 < H) & (w2 >= 0) & (w2 < W);
       const float g = ok ? dyp[-(dh * W + dw)] : 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; j++) acc[j] = fmaf(g, wreg[t][j], acc[j]);
+      for (int j = 0; j < 4; j++) acc2[j] = __ffma2_rn(f2(g), wreg[t][j], acc2[j]);
     }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { acc[2 * j] = acc2[j].x; acc[2 * j + 1] = acc2[j].y; }
     if (SIG) {
       float sv[8];
       load8(x + pix * ldx + cv * 8, sv);
@@ -378,11 +390,11 @@ __global__ void __launch_bounds__(256, 2) conv_c1_bwd_weight32_kernel(const floa
   const int cv = threadIdx.x, ry = threadIdx.y, rows = blockDim.y;       // blockDim = (4, 64)
   const int spr = (W + C1_STRIP - 1) / C1_STRIP;                           // strips per image row
   const long long nstrips = (long long)B * H * spr;
-  float acc[10][8];
+  float2 acc[10][4];                      // channel pairs (FFMA2)
 #pragma unroll
   for (int q = 0; q < 10; q++)
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[q][j] = 0.f;
+    for (int j = 0; j < 4; j++) acc[q][j] = make_float2(0.f, 0.f);
   for (long long sidx = (long long)blockIdx.x * rows + ry; sidx < nstrips; sidx += (long long)gridDim.x * rows) {
     const int sw = (int)(sidx % spr);
     const long long bh = sidx / spr;                     // b * H + h
@@ -414,20 +426,26 @@ __global__ void __launch_bounds__(256, 2) conv_c1_bwd_weight32_kernel(const floa
       }
       float v[8];
       unpack8(raw, v);
+      float2 v2[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) v2[j] = make_float2(v[2 * j], v[2 * j + 1]);
 #pragma unroll
       for (int t = 0; t < 9; t++) {
-        const float g = G[2 - t / 3][2 - t % 3];
+        const float2 g = f2(G[2 - t / 3][2 - t % 3]);
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[t][j] = fmaf(g, v[j], acc[t][j]);
+        for (int j = 0; j < 4; j++) acc[t][j] = __ffma2_rn(g, v2[j], acc[t][j]);
       }
-      if (cv == 0) acc[9][0] += G[1][1];
+      if (cv == 0) acc[9][0].x += G[1][1];
     }
   }
   const int cvec = 4, Cin = C1_CIN;
 #pragma unroll
   for (int q = 0; q < 10; q++) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) red[(ry * cvec + cv) * 8 + j] = acc[q][j];
+    for (int j = 0; j < 4; j++) {
+      red[(ry * cvec + cv) * 8 + 2 * j] = acc[q][j].x;
+      red[(ry * cvec + cv) * 8 + 2 * j + 1] = acc[q][j].y;
+    }
     __syncthreads();
     const int t = ry * cvec + cv, nt = rows * cvec;
     for (int cc = t; cc < Cin; cc += nt) {

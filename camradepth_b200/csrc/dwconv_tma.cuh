@@ -44,6 +44,12 @@ __device__ __forceinline__ void lds8_unpack(uint32_t addr, float (&v)[4]) {
   v[0] = __uint_as_float(lo << 16); v[1] = __uint_as_float(lo & 0xffff0000u);
   v[2] = __uint_as_float(hi << 16); v[3] = __uint_as_float(hi & 0xffff0000u);
 }
+// the same four channels as two register pairs (operands of FFMA2 / FMUL2)
+__device__ __forceinline__ void lds8_unpack2(uint32_t addr, float2 (&v)[2]) {
+  float t[4];
+  lds8_unpack(addr, t);
+  v[0] = make_float2(t[0], t[1]); v[1] = make_float2(t[2], t[3]);
+}
 __device__ __forceinline__ void stg8_bf16(bf16* p, const float (&v)[4]) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
   uint2 r;
@@ -101,18 +107,19 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap m_a, const __grid_constant
   const int cg = tid & 15, col = tid >> 4;
   const int c = c0 + cg * 4;
   const bool col_ok = col < p.TW;
-  float wt[9][4], bs[4];
+  // four channels = two register pairs: the taps run on FFMA2 (two channels per instruction, same per-lane arithmetic)
+  float2 wt[9][2], bs[2];
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
-    bs[j] = (!BWD && p.bias) ? p.bias[c + j] : 0.f;
+  for (int j = 0; j < 2; j++) {
+    bs[j] = (!BWD && p.bias) ? make_float2(p.bias[c + 2 * j], p.bias[c + 2 * j + 1]) : make_float2(0.f, 0.f);
 #pragma unroll
-    for (int t = 0; t < 9; t++) wt[t][j] = p.w[(c + j) * 9 + t];
+    for (int t = 0; t < 9; t++) wt[t][j] = make_float2(p.w[(c + 2 * j) * 9 + t], p.w[(c + 2 * j + 1) * 9 + t]);
   }
-  float acc[BWD ? 10 : 1][4];
+  float2 acc[BWD ? 10 : 1][2];
 #pragma unroll
   for (int q = 0; q < (BWD ? 10 : 1); q++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) acc[q][j] = 0.f;
+    for (int j = 0; j < 2; j++) acc[q][j] = make_float2(0.f, 0.f);
 
   const uint32_t pix_a = (uint32_t)((p.TW + 2) * 128), pix_x = (uint32_t)(p.TW * 128);
   int it = 0;
@@ -123,31 +130,35 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap m_a, const __grid_constant
     const int nb = (h1 - h0 + 2 + DW_RH - 1) / DW_RH;
     const int wcol = strip * p.TW + col;
     const bool valid = col_ok && wcol < p.W;
-    float a[4], sh[4], kfull[4], ktop[4], kbot[4];
+    float2 a[2], sh[2], kfull[2], ktop[2], kbot[2];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const long long bc = (long long)b * p.C + c + j;
-      a[j] = p.ab[bc * 2];
-      sh[j] = p.ab[bc * 2 + 1];
+    for (int j = 0; j < 2; j++) {
+      const long long bc = (long long)b * p.C + c + 2 * j;
+      a[j] = make_float2(p.ab[bc * 2], p.ab[bc * 2 + 2]);
+      sh[j] = make_float2(p.ab[bc * 2 + 1], p.ab[bc * 2 + 3]);
       if (!BWD) {
         // constant term: bias + sh * (sum of the taps that land inside the image for this column)
         const bool l = wcol > 0, r = wcol < p.W - 1;
-        float wr[3];
+        float2 wr[3];
 #pragma unroll
-        for (int kh = 0; kh < 3; kh++) wr[kh] = (l ? wt[kh * 3][j] : 0.f) + wt[kh * 3 + 1][j] + (r ? wt[kh * 3 + 2][j] : 0.f);
-        kfull[j] = fmaf(sh[j], wr[0] + wr[1] + wr[2], bs[j]);
-        ktop[j] = sh[j] * wr[0];
-        kbot[j] = sh[j] * wr[2];
+        for (int kh = 0; kh < 3; kh++) {
+          const float2 wl = l ? wt[kh * 3][j] : make_float2(0.f, 0.f), wrr = r ? wt[kh * 3 + 2][j] : make_float2(0.f, 0.f);
+          wr[kh] = make_float2(wl.x + wt[kh * 3 + 1][j].x + wrr.x, wl.y + wt[kh * 3 + 1][j].y + wrr.y);
+        }
+        kfull[j] = make_float2(fmaf(sh[j].x, wr[0].x + wr[1].x + wr[2].x, bs[j].x),
+                               fmaf(sh[j].y, wr[0].y + wr[1].y + wr[2].y, bs[j].y));
+        ktop[j] = make_float2(sh[j].x * wr[0].x, sh[j].y * wr[0].y);
+        kbot[j] = make_float2(sh[j].x * wr[2].x, sh[j].y * wr[2].y);
       }
     }
     bf16* ob = p.out + (((long long)b * p.H) * p.W + wcol) * p.C + c;
-    float win[3][3][4];
+    float2 win[3][3][2];
 #pragma unroll
     for (int r = 0; r < 3; r++)
 #pragma unroll
       for (int d = 0; d < 3; d++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) win[r][d][j] = 0.f;
+        for (int j = 0; j < 2; j++) win[r][d][j] = make_float2(0.f, 0.f);
 
     for (int k = 0; k < nb; k++, it++) {
       const int s = it % S;
@@ -160,51 +171,54 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap m_a, const __grid_constant
         for (int r = 0; r < DW_RH; r++) {
           // newest row goes to window slot r % 3 (DW_RH is a multiple of 3, so the slot is static)
 #pragma unroll
-          for (int d = 0; d < 3; d++) lds8_unpack(sa + r * pix_a + d * 128, win[r % 3][d]);
+          for (int d = 0; d < 3; d++) lds8_unpack2(sa + r * pix_a + d * 128, win[r % 3][d]);
           const int ii = DW_RH * k + r;
           const int h = h0 + ii - 2;
           if (ii >= 2 && h < h1 && valid) {
-            const float (&top)[3][4] = win[(r + 1) % 3];
-            const float (&mid)[3][4] = win[(r + 2) % 3];
-            const float (&bot)[3][4] = win[r % 3];
-            float o[4];
+            const float2 (&top)[3][2] = win[(r + 1) % 3];
+            const float2 (&mid)[3][2] = win[(r + 2) % 3];
+            const float2 (&bot)[3][2] = win[r % 3];
+            float2 o[2];
             if (!BWD) {
 #pragma unroll
-              for (int j = 0; j < 4; j++) {
-                float t = 0.f;
+              for (int j = 0; j < 2; j++) {
+                float2 t = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
-                  t = fmaf(wt[d][j], top[d][j], t);
-                  t = fmaf(wt[3 + d][j], mid[d][j], t);
-                  t = fmaf(wt[6 + d][j], bot[d][j], t);
+                  t = __ffma2_rn(wt[d][j], top[d][j], t);
+                  t = __ffma2_rn(wt[3 + d][j], mid[d][j], t);
+                  t = __ffma2_rn(wt[6 + d][j], bot[d][j], t);
                 }
-                float kk = kfull[j];
-                if (h == 0) kk -= ktop[j];
-                if (h == p.H - 1) kk -= kbot[j];
-                o[j] = fmaf(a[j], t, kk);
+                float2 kk = kfull[j];
+                if (h == 0) { kk.x -= ktop[j].x; kk.y -= ktop[j].y; }
+                if (h == p.H - 1) { kk.x -= kbot[j].x; kk.y -= kbot[j].y; }
+                o[j] = __ffma2_rn(a[j], t, kk);
               }
             } else {
-              float xv[4];
-              lds8_unpack(sx + r * pix_x, xv);
+              float2 xv[2];
+              lds8_unpack2(sx + r * pix_x, xv);
 #pragma unroll
-              for (int j = 0; j < 4; j++) {
-                const float xn = fmaf(a[j], xv[j], sh[j]);
-                float t = 0.f;
+              for (int j = 0; j < 2; j++) {
+                const float2 xn = __ffma2_rn(a[j], xv[j], sh[j]);
+                float2 t = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
                   // window (row rr, column d) holds dy[q - tap] for tap (kh, kw) = (2 - rr, 2 - d)
-                  t = fmaf(wt[6 + (2 - d)][j], top[d][j], t);
-                  t = fmaf(wt[3 + (2 - d)][j], mid[d][j], t);
-                  t = fmaf(wt[(2 - d)][j], bot[d][j], t);
-                  acc[6 + (2 - d)][j] = fmaf(top[d][j], xn, acc[6 + (2 - d)][j]);
-                  acc[3 + (2 - d)][j] = fmaf(mid[d][j], xn, acc[3 + (2 - d)][j]);
-                  acc[(2 - d)][j] = fmaf(bot[d][j], xn, acc[(2 - d)][j]);
+                  t = __ffma2_rn(wt[6 + (2 - d)][j], top[d][j], t);
+                  t = __ffma2_rn(wt[3 + (2 - d)][j], mid[d][j], t);
+                  t = __ffma2_rn(wt[(2 - d)][j], bot[d][j], t);
+                  acc[6 + (2 - d)][j] = __ffma2_rn(top[d][j], xn, acc[6 + (2 - d)][j]);
+                  acc[3 + (2 - d)][j] = __ffma2_rn(mid[d][j], xn, acc[3 + (2 - d)][j]);
+                  acc[(2 - d)][j] = __ffma2_rn(bot[d][j], xn, acc[(2 - d)][j]);
                 }
-                acc[9][j] += mid[1][j];
+                acc[9][j] = __fadd2_rn(acc[9][j], mid[1][j]);
                 o[j] = t;
               }
             }
-            stg8_bf16(ob + (long long)h * p.W * p.C, o);
+            {
+              const float ov[4] = {o[0].x, o[0].y, o[1].x, o[1].y};
+              stg8_bf16(ob + (long long)h * p.W * p.C, ov);
+            }
           }
         }
       }
@@ -220,7 +234,10 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap m_a, const __grid_constant
 #pragma unroll
     for (int q = 0; q < 10; q++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) red[(q * DW_COLS + col) * DW_CH + cg * 4 + j] = acc[q][j];
+      for (int j = 0; j < 2; j++) {
+        red[(q * DW_COLS + col) * DW_CH + cg * 4 + 2 * j] = acc[q][j].x;
+        red[(q * DW_COLS + col) * DW_CH + cg * 4 + 2 * j + 1] = acc[q][j].y;
+      }
     asm volatile("bar.sync 1, %0;" ::"n"(DW_CONSUMERS) : "memory");
     for (int e = tid; e < 10 * DW_CH; e += DW_CONSUMERS) {
       const int q = e / DW_CH, ch = e - q * DW_CH;

@@ -156,7 +156,12 @@ gn_stream_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__
         } else if (MODE == ST_AFFINE) {
           if (p.act == CRD_ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) g[j] = gelu_f(fmaf(a[j], g[j], sh[j])) * k1[j];
+            for (int j = 0; j < 8; j += 2) {       // two channels per FFMA2 / FMUL2
+              const float2 z = __ffma2_rn(make_float2(a[j], a[j + 1]), make_float2(g[j], g[j + 1]),
+                                          make_float2(sh[j], sh[j + 1]));
+              const float2 y = __fmul2_rn(gelu2(z), make_float2(k1[j], k1[j + 1]));
+              g[j] = y.x; g[j + 1] = y.y;
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 8; j++) g[j] = st_act_fwd(fmaf(a[j], g[j], sh[j]), p.act) * k1[j];
@@ -164,11 +169,22 @@ gn_stream_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__
           store8(outb + q * p.ldo, g);
         } else {
           unpack8(r1[r], v);
+          if (p.act == CRD_ACT_GELU) {
+            // the activation derivative two channels at a time; g then holds dz and the loop below runs with it
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              const float2 dz0 = __ffma2_rn(make_float2(k1[j], k1[j + 1]), make_float2(g[j], g[j + 1]),
+                                            make_float2(k0[j], k0[j + 1]));
+              const float2 z = __ffma2_rn(make_float2(a[j], a[j + 1]), make_float2(v[j], v[j + 1]),
+                                          make_float2(sh[j], sh[j + 1]));
+              const float2 dz = __fmul2_rn(dz0, gelu_grad2(z));
+              g[j] = dz.x; g[j + 1] = dz.y;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 8; j++) {
-            float dz = fmaf(k1[j], g[j], k0[j]);
-            if (p.act == CRD_ACT_GELU) dz *= gelu_grad_f(fmaf(a[j], v[j], sh[j]));
-            else if (p.act != CRD_ACT_NONE) dz *= st_act_bwd(fmaf(a[j], v[j], sh[j]), p.act);
+            float dz = p.act == CRD_ACT_GELU ? g[j] : fmaf(k1[j], g[j], k0[j]);
+            if (p.act != CRD_ACT_NONE && p.act != CRD_ACT_GELU) dz *= st_act_bwd(fmaf(a[j], v[j], sh[j]), p.act);
             if (MODE == ST_BWD_REDUCE) {
               s0[j] += dz;
               s1[j] = fmaf(dz, v[j], s1[j]);
