@@ -171,8 +171,9 @@ __global__ void conv_c1_fwd_kernel(const T* __restrict__ x, const float* __restr
 // The generic kernels above / below spend ~1700 (forward) and ~470 (input gradient) instructions per thread on index
 // arithmetic, per-tap weight loads and one load per (tap, 8 channels): ncu showed L1 at 91 % / issue slots at 78 % for
 // 164 MB tensors that stream in 30 us.  These variants share the loads:
-//   forward : a thread owns FOUR adjacent output pixels of a row; per (input row, 8-channel group) it loads the six
-//             input columns once and the 3x8 weights once for 96 FMAs (18 instead of 36 sixteen-byte loads per pixel)
+//   forward : four lanes own FOUR adjacent output pixels of a row, one lane per 8-channel group; per input row a lane
+//             loads its 16 bytes of the six input columns once for 96 FMAs against weights held in registers (18
+//             instead of 36 sixteen-byte loads per pixel, each warp load = 8 runs of 64 contiguous bytes)
 //   backward: a thread keeps the 9x8 weights of ITS channel group in registers over the whole grid-stride loop and
 //             multiplies by the sigmoid derivative on the way out (no dsg buffer, no separate sigmoid pass)
 constexpr int C1_CIN = 32;
