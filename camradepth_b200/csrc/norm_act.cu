@@ -50,7 +50,11 @@ __global__ void gn_finalize_kernel(const float* __restrict__ sums, const float* 
   const int b = blockIdx.x;
   const int cpg = C / G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int g = warp; g < G; g += nw) {      // one warp per group
+  // blockIdx.y = slice of whole groups (gridDim.y slices): wide layers (512 / 1024 channels) no longer walk 4-8 groups
+  // per warp one after the other
+  const int gps = (G + gridDim.y - 1) / gridDim.y;
+  const int g0 = blockIdx.y * gps, g1 = min(G, g0 + gps);
+  for (int g = g0 + warp; g < g1; g += nw) {      // one warp per group
     double s = 0.0, ss = 0.0;
     for (int j = lane; j < cpg; j += 32) {
       const float* p = sums + ((long long)b * C + g * cpg + j) * 2;
@@ -73,7 +77,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ sums, const float* 
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  for (int c = g0 * cpg + threadIdx.x; c < g1 * cpg; c += blockDim.x) {
     const int g = c / cpg;
     const float a = gamma[c] * gs[2 * g + 1];
     const float bb = beta[c] - gs[2 * g] * a;
@@ -205,7 +209,9 @@ __global__ void gn_bwd_finalize_kernel(const float* __restrict__ pq, const float
   const int b = blockIdx.x;
   const int cpg = C / G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int g = warp; g < G; g += nw) {
+  const int gps = (G + gridDim.y - 1) / gridDim.y;          // blockIdx.y = slice of whole groups
+  const int g0 = blockIdx.y * gps, g1 = min(G, g0 + gps);
+  for (int g = g0 + warp; g < g1; g += nw) {
     const float mu = mean_rstd[((long long)b * G + g) * 2 + 0];
     const float r = mean_rstd[((long long)b * G + g) * 2 + 1];
     double t1 = 0.0, t2 = 0.0;
@@ -228,7 +234,7 @@ __global__ void gn_bwd_finalize_kernel(const float* __restrict__ pq, const float
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  for (int c = g0 * cpg + threadIdx.x; c < g1 * cpg; c += blockDim.x) {
     const int g = c / cpg;
     const float mu = mean_rstd[((long long)b * G + g) * 2 + 0];
     const float r = mean_rstd[((long long)b * G + g) * 2 + 1];
@@ -325,12 +331,18 @@ extern "C" int crd_chan_stats(const void* x, int dtype, float* sums, int B, long
   return 0;
 }
 
+// slices of whole groups per sample for the finalize kernels: one per 256 channels and at most one per 8 groups
+static int gn_fin_slices(int C, int G) {
+  int s = C / 256;
+  if (s > G / 8) s = G / 8;
+  return s < 1 ? 1 : s;
+}
 extern "C" int crd_gn_finalize(const float* sums, const float* gamma, const float* beta, float* ab,
                                float* mean_rstd, float* xbar, int B, int C, int G, long long N, float eps,
                                crd_stream_t stream) {
   CRD_REQUIRE(G > 0 && C % G == 0);
   if (B == 0) return 0;
-  crd_launch(gn_finalize_kernel, dim3(B), dim3(256), 2 * G * sizeof(float), (cudaStream_t)stream, sums, gamma, beta, ab, mean_rstd, xbar, B, C, G, N, eps);
+  crd_launch(gn_finalize_kernel, dim3(B, gn_fin_slices(C, G)), dim3(256), 2 * G * sizeof(float), (cudaStream_t)stream, sums, gamma, beta, ab, mean_rstd, xbar, B, C, G, N, eps);
   CRD_LAUNCH_CHECK();
   return 0;
 }
@@ -387,7 +399,7 @@ extern "C" int crd_gn_bwd_finalize(const float* pq, const float* mean_rstd, cons
                                    crd_stream_t stream) {
   CRD_REQUIRE(G > 0 && C % G == 0);
   if (B == 0) return 0;
-  crd_launch(gn_bwd_finalize_kernel, dim3(B), dim3(256), 2 * G * sizeof(float), (cudaStream_t)stream, pq, mean_rstd, gamma, coef, dgamma, dbeta, B, C, G, N);
+  crd_launch(gn_bwd_finalize_kernel, dim3(B, gn_fin_slices(C, G)), dim3(256), 2 * G * sizeof(float), (cudaStream_t)stream, pq, mean_rstd, gamma, coef, dgamma, dbeta, B, C, G, N);
   CRD_LAUNCH_CHECK();
   return 0;
 }
