@@ -140,6 +140,30 @@ class GraphedDataParallelStep(GraphedTrainStep):
 
     TAGS = ("decoder", "stage3", "stage2", "stage1", "stage0")
 
+    @classmethod
+    def plan_segments(cls, one_graph, cuts="stage1"):
+        """Phases of one step grouped into CUDA graphs.  `cuts`: comma-separated bucket tags after which a new graph
+        starts.  The number of cuts does not change the step time measurably (profiles/r2_dp_overhead_2gpu.txt); every
+        bucket left to the last backward graph is exposed, so the default cuts once, after encoder stage 2: 81 of the
+        88 MB travel while the stage-1 backward (~4 ms) still runs.  The forward always ends its own graph when there
+        are several (the loss exchange sits behind it)."""
+        if one_graph:
+            return [["fwd", "loss"] + list(cls.TAGS[1:]) + ["opt"]]
+        cutset = set(filter(None, (cuts or "").split(",")))
+        unknown = cutset - set(cls.TAGS[1:])
+        if unknown:
+            raise ValueError(f"CAMRADEPTH_DP_CUTS: unknown bucket tag(s) {sorted(unknown)}; known: {cls.TAGS[1:]}")
+        segments, cur = [["fwd"]], ["loss"]
+        for t in cls.TAGS[1:]:
+            cur.append(t)
+            if t in cutset:
+                segments.append(cur)
+                cur = []
+        if cur:
+            segments.append(cur)
+        segments.append(["opt"])
+        return segments
+
     def __init__(self, model, optimizer, example_batch, scheduler=None, update_interval=1, process_group=None,
                  global_loss_mean=None, warmup=2):
         import torch.distributed as dist
@@ -181,22 +205,8 @@ class GraphedDataParallelStep(GraphedTrainStep):
         torch.cuda.synchronize()
         self._ranges = {t: bucket_ranges(eng.names, eng.pg_offsets, t) for t in self.TAGS}
         # ---- capture
-        if self.world == 1 or "onegraph" in self._debug:
-            segments = [["fwd", "loss"] + list(self.TAGS[1:]) + ["opt"]]
-        else:
-            # cut points of the backward program (tags after which a new graph starts).  Every graph boundary costs
-            # ~0.1 ms (profiles/r2_dp_overhead_2gpu.txt), every bucket left to the last graph is exposed: one cut
-            # after encoder stage 2 sends 81 of the 88 MB while the stage-1 backward (~4 ms) still runs.
-            cuts = set(filter(None, os.environ.get("CAMRADEPTH_DP_CUTS", "stage1").split(",")))
-            segments, cur = [["fwd"]], ["loss"]
-            for t in self.TAGS[1:]:
-                cur.append(t)
-                if t in cuts:
-                    segments.append(cur)
-                    cur = []
-            if cur:
-                segments.append(cur)
-            segments.append(["opt"])
+        segments = self.plan_segments(self.world == 1 or "onegraph" in self._debug,
+                                      os.environ.get("CAMRADEPTH_DP_CUTS", "stage1"))
         pool = torch.cuda.graph_pool_handle()
         self.graphs = []
         for seg in segments:

@@ -115,3 +115,16 @@ def test_synthetic_batch_contract():
     assert torch.equal(minpool_gt(b["gt_final"]), O.minpool(b["gt_final"]))
     b2 = make_batch(2, 64, 96, seed=0)
     assert torch.equal(b["image"], b2["image"])
+
+
+def test_weight_pack_brick_count_is_a_pure_host_function():
+    """crd_weight_pack_blocks (how many blocks one item of a crd_weight_pack_batch table owns) needs no GPU: one brick
+    per (<= 64 output channels) x (<= 64 input channels) x all taps with at most 8192 elements."""
+    from camradepth_b200._lib import load
+    lib = load()
+    f = lib.crd_weight_pack_blocks
+    assert f(128, 296, 9) == ((128 + 13) // 14) * 5          # 64 ci x 9 taps = 576 per row -> 14 output channels per brick
+    assert f(1024, 128, 1) == 16 * 2                          # 1x1: 64 x 64 bricks
+    assert f(64, 7, 49) == 3                                  # 7 ci x 49 taps = 343 per row -> 23 output channels
+    assert f(1, 32, 9) == 1
+    assert f(0, 32, 9) < 0 and f(8, 8, 129) < 0               # rejected: empty / more taps than a brick row can hold

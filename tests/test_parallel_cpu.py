@@ -122,3 +122,19 @@ def test_global_masked_mean_convention_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_graph_segments_of_the_data_parallel_step():
+    """Host logic of graphs.GraphedDataParallelStep: which phases share a CUDA graph for a given set of cut points."""
+    from camradepth_b200.graphs import GraphedDataParallelStep as G
+    assert G.plan_segments(True) == [["fwd", "loss", "stage3", "stage2", "stage1", "stage0", "opt"]]
+    assert G.plan_segments(False) == [["fwd"], ["loss", "stage3", "stage2", "stage1"], ["stage0"], ["opt"]]
+    assert G.plan_segments(False, "") == [["fwd"], ["loss", "stage3", "stage2", "stage1", "stage0"], ["opt"]]
+    assert G.plan_segments(False, "stage3,stage2,stage1,stage0") == \
+        [["fwd"], ["loss", "stage3"], ["stage2"], ["stage1"], ["stage0"], ["opt"]]
+    for segs in (G.plan_segments(False), G.plan_segments(False, "stage2,stage0")):
+        flat = [p for s in segs for p in s]
+        assert flat == ["fwd", "loss", "stage3", "stage2", "stage1", "stage0", "opt"]      # every phase once, in order
+    import pytest
+    with pytest.raises(ValueError):
+        G.plan_segments(False, "stage7")
