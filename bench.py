@@ -438,8 +438,9 @@ def main():
         elif world == 1:
             launch = "one CUDA graph per step"
         else:
-            launch = (f"{n_graphs} CUDA graphs per step cut at the gradient-bucket boundaries; each bucket's NCCL all-reduce "
-                      "runs on NCCL's stream while the next graph (backward of the next encoder stage) executes")
+            launch = (f"{n_graphs} CUDA graphs per step (forward | losses + backward down to encoder stage 2 | rest of the "
+                      "backward | optimizer); the NCCL all-reduce of the gradient buckets a graph completed runs on NCCL's "
+                      "stream while the next graph executes; loss sums all-reduced for global masked means")
         out = {
             "metric": "train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps,
             "warmup": a.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
