@@ -5,7 +5,7 @@
 Tolerances (SURVEY.md §8c calibration):
   fp32 mode : final depth rel-L2 <= 1e-4; per-tensor grad rel-L2 <= 2e-3 (argmax-routed attn tensors 2e-2)
   bf16 mode : final depth rel-L2 <= 1e-2; global grad rel-L2 <= 3e-2, cosine >= 0.999;
-              attn q/k/sr/norm tensors (argmax flips under bf16 rounding) cosine >= 0.9 reported separately
+              attn q/k/sr/norm tensors (argmax flips under bf16 rounding) cosine >= 0.95 reported separately
 """
 import json
 import os
@@ -99,14 +99,18 @@ def test_model_matches_reference_golden(path, precision):
         cos = float(torch.nn.functional.cosine_similarity(mine.double(), gs.double(), dim=0))
         report["full_grads"][n] = (e, cos)
         if any(k in n for k in ATTN_KEYS):
-            assert cos > (0.999 if precision == "fp32" else 0.9), (n, e, cos)
+            # bf16: observed 0.983 .. 0.9996 over the six fixtures (profiles/r2_parity_report.jsonl); a wrong tap
+            # order / transposition in the sr or q / k gradients gives |cos| < 0.5.  The bf16-only kernels behind these
+            # tensors (strided implicit GEMM, depth-to-space data gradient, tcgen05 score) are pinned one by one in
+            # test_gpu_tc.py / test_gpu_ops.py; fp32 mode pins the program around them at 0.999.
+            assert cos > (0.999 if precision == "fp32" else 0.95), (n, e, cos)
         else:
             assert e < gt, (n, e, cos)
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, "parity_report.jsonl"), "a") as fh:
         fh.write(json.dumps(report) + "\n")
     assert worst[1] < (2e-3 if precision == "fp32" else 8e-2), worst
-    assert worst_attn[1] < (2e-2 if precision == "fp32" else 0.35), worst_attn
+    assert worst_attn[1] < (2e-2 if precision == "fp32" else 0.3), worst_attn      # observed <= 0.11
 
 
 @pytest.mark.parametrize("path", FILES[:1], ids=lambda p: os.path.basename(p))
